@@ -36,13 +36,19 @@ NEG_INF = -np.inf
 
 
 def log_softmax_rows(x: np.ndarray) -> np.ndarray:
-    """Row-wise log-softmax in float64 (warp-ctc softmaxes internally: README.md:168)."""
+    """Row-wise log of the softmax *probabilities*, float64.
+
+    warp-ctc softmaxes internally (reference README.md:168) and keeps probabilities, taking
+    log(p) at each use, so a logit far enough below the row max has p == 0 and log p == -inf
+    (fp32: gap > ~103; here in float64: gap > ~745).  Following that form (rather than
+    z - log(sum)) keeps the oracle's behaviour on -1e30-style inputs the same as the reference's.
+    """
     x = np.asarray(x, dtype=np.float64)
     m = x.max(axis=-1, keepdims=True)
     m = np.where(np.isfinite(m), m, 0.0)
-    z = x - m
+    e = np.exp(x - m)
     with np.errstate(divide="ignore"):
-        return z - np.log(np.exp(z).sum(axis=-1, keepdims=True))
+        return np.log(e / e.sum(axis=-1, keepdims=True))
 
 
 def count_repeats(labels: np.ndarray) -> int:
