@@ -1,0 +1,104 @@
+"""ctypes binding of libctc_b200.so (include/ctc.h).  There is NO fallback: if the library is missing
+or has not been built for this tree, every entry point raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "lib", "libctc_b200.so")
+
+CTC_STATUS_SUCCESS = 0
+CTC_GPU = 1
+FLAG_NO_SYNC = 0x1
+FLAG_MODE_THROUGHPUT = 1 << 8
+FLAG_MODE_LATENCY = 2 << 8
+
+UTT_INFEASIBLE, UTT_INF_COST, UTT_BAD_LABEL, UTT_RANGE = 1, 2, 4, 8
+
+
+class _OptUnion(ctypes.Union):
+    _fields_ = [("num_threads", ctypes.c_uint), ("stream", ctypes.c_void_p)]
+
+
+class CtcOptions(ctypes.Structure):
+    """struct ctcOptions of include/ctc.h (passed by value)."""
+    _anonymous_ = ("u",)
+    _fields_ = [("loc", ctypes.c_int), ("u", _OptUnion), ("blank_label", ctypes.c_int)]
+
+
+class CtcB200Call(ctypes.Structure):
+    """struct ctcB200Call of include/ctc.h."""
+    _fields_ = [
+        ("activations", ctypes.c_void_p),
+        ("act_stride_t", ctypes.c_longlong),
+        ("act_stride_b", ctypes.c_longlong),
+        ("gradients", ctypes.c_void_p),
+        ("flat_labels", ctypes.c_void_p),
+        ("label_lengths", ctypes.c_void_p),
+        ("input_lengths", ctypes.c_void_p),
+        ("alphabet_size", ctypes.c_int),
+        ("minibatch", ctypes.c_int),
+        ("max_time", ctypes.c_int),
+        ("blank_label", ctypes.c_int),
+        ("grad_scale", ctypes.c_float),
+        ("costs_host", ctypes.c_void_p),
+        ("costs_device", ctypes.c_void_p),
+        ("status_host", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", ctypes.c_size_t),
+        ("stream", ctypes.c_void_p),
+        ("flags", ctypes.c_uint),
+    ]
+
+
+EXPORTS = ("get_warpctc_version", "ctcGetStatusString", "compute_ctc_loss", "get_workspace_size",
+           "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info")
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -m aes_lac_2018_b200.build`).  There is no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild it")
+    lib.get_warpctc_version.restype = ctypes.c_int
+    lib.ctcGetStatusString.restype = ctypes.c_char_p
+    lib.ctcGetStatusString.argtypes = [ctypes.c_int]
+    lib.ctc_b200_last_error.restype = ctypes.c_char_p
+    lib.ctc_b200_info.restype = ctypes.c_int
+    lib.ctc_b200_info.argtypes = [ctypes.POINTER(ctypes.c_ulonglong)]
+    lib.compute_ctc_loss.restype = ctypes.c_int
+    lib.compute_ctc_loss.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, CtcOptions]
+    lib.get_workspace_size.restype = ctypes.c_int
+    lib.get_workspace_size.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, CtcOptions,
+        ctypes.POINTER(ctypes.c_size_t)]
+    lib.ctc_b200_workspace_size.restype = ctypes.c_int
+    lib.ctc_b200_workspace_size.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_size_t)]
+    lib.ctc_b200_compute.restype = ctypes.c_int
+    lib.ctc_b200_compute.argtypes = [ctypes.POINTER(CtcB200Call)]
+    _lib = lib
+    return lib
+
+
+def status_string(lib, st: int) -> str:
+    return f"{lib.ctcGetStatusString(st).decode()} ({lib.ctc_b200_last_error().decode()})"
+
+
+def launch_count() -> int:
+    n = ctypes.c_ulonglong(0)
+    load().ctc_b200_info(ctypes.byref(n))
+    return int(n.value)

@@ -1,0 +1,332 @@
+// ctc_abi.cu -- host side of libctc_b200.so: the C ABI declared in include/ctc.h.
+//
+// Replaces, for the GPU location, what warp-ctc's src/ctc_entrypoint.cu + GpuCTC::cost_and_grad do
+// behind `warpctc_pytorch.CTCLoss` (reference train.py:12/179, codes/engine.py:22, codes/metrics.py:51):
+// argument validation, per-utterance metadata, workspace carve-up, kernel dispatch, cost read-back.
+// Nothing here allocates device memory; everything lives in the caller's workspace.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ctc.h"
+#include "ctc_fused.cuh"
+
+namespace {
+
+using namespace ctcb200;
+
+thread_local std::string g_last_error;
+thread_local unsigned long long g_launches = 0;
+
+ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
+{
+    g_last_error = msg;
+    return st;
+}
+
+// ---- kernel variants --------------------------------------------------------------------------
+// (NS states per thread, W warps per utterance, K timesteps per chunk).  SP = 32*NS*W padded states;
+// an utterance with L labels fits when SP >= 2L + 2.
+struct Variant {
+    int NS, W, K;
+    void (*kernel)(const FusedParams);
+    int max_label() const { return (32 * NS * W) / 2 - 1; }
+    int sp() const { return 32 * NS * W; }
+};
+
+#define CTC_VARIANT(NS, W, K) Variant{NS, W, K, ctc_fused_kernel<NS, W, K>}
+
+// Throughput ladder: one warp per utterance, as few states per thread as fit.
+const Variant kThroughput[] = {
+    CTC_VARIANT(2, 1, 16),  CTC_VARIANT(4, 1, 16),  CTC_VARIANT(6, 1, 16),  CTC_VARIANT(8, 1, 16),
+    CTC_VARIANT(10, 1, 16), CTC_VARIANT(12, 1, 16), CTC_VARIANT(14, 1, 16), CTC_VARIANT(16, 1, 16),
+    CTC_VARIANT(16, 2, 16), CTC_VARIANT(16, 4, 8),  CTC_VARIANT(16, 8, 4),
+};
+// Latency ladder (few utterances in flight): more warps per utterance, fewer states per thread.
+const Variant kLatency[] = {
+    CTC_VARIANT(2, 1, 16), CTC_VARIANT(2, 2, 16), CTC_VARIANT(2, 4, 16), CTC_VARIANT(4, 4, 16),
+    CTC_VARIANT(4, 8, 16), CTC_VARIANT(8, 8, 8),  CTC_VARIANT(16, 8, 4),
+};
+constexpr int kNumThroughput = sizeof(kThroughput) / sizeof(Variant);
+constexpr int kNumLatency = sizeof(kLatency) / sizeof(Variant);
+constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
+constexpr int kMaxSmem = 227 * 1024;
+
+const Variant *pick(const Variant *ladder, int n, int L)
+{
+    for (int i = 0; i < n; ++i)
+        if (ladder[i].max_label() >= L) return &ladder[i];
+    return nullptr;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Plan {
+    int B = 0, T_max = 0, V = 0;
+    bool latency = false;
+    std::vector<int> meta;                   // [label_off B | label_len B | act_len B | utt_ids B]
+    struct Launch { const Variant *v; int first, count; size_t ckpt_off; long long ckpt_stride; int smem; };
+    std::vector<Launch> launches;
+    long long total_labels = 0;
+    size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_ckpt = 0, total = 0;
+};
+
+// forced_w: 0 = automatic ladder choice; otherwise use the latency ladder entry with that W where possible
+ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V, int B, int T_max,
+                      bool want_grad, int mode, Plan &plan)
+{
+    if (!label_lengths || !input_lengths) return fail(CTC_STATUS_INVALID_VALUE, "null length array");
+    if (V <= 0 || B <= 0 || T_max < 0) return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
+    plan.B = B; plan.T_max = T_max; plan.V = V;
+    plan.meta.assign((size_t)4 * B, 0);
+    int *label_off = plan.meta.data(), *label_len = label_off + B, *act_len = label_len + B,
+        *utt_ids = act_len + B;
+    long long off = 0;
+    int max_L = 0;
+    for (int b = 0; b < B; ++b) {
+        const int L = label_lengths[b], T = input_lengths[b];
+        if (L < 0 || T < 0) return fail(CTC_STATUS_INVALID_VALUE, "negative length");
+        if (T > T_max) return fail(CTC_STATUS_INVALID_VALUE, "input_lengths[b] exceeds max_time");
+        if (L > kMaxLabelLen)
+            return fail(CTC_STATUS_UNKNOWN_ERROR, "label sequence longer than 2047 is not supported");
+        if (off > 0x7fffffffLL - L) return fail(CTC_STATUS_INVALID_VALUE, "too many labels");
+        label_off[b] = (int)off; label_len[b] = L; act_len[b] = T;
+        off += L;
+        max_L = std::max(max_L, L);
+    }
+    plan.total_labels = off;
+
+    // mode: 0 auto, 1 throughput ladder, 2 latency ladder.  Auto: with fewer utterances than ~2 per SM
+    // the T-serial chain is the bound, so spend more warps per utterance.
+    plan.latency = (mode == 2) || (mode == 0 && B <= 296);
+    const Variant *ladder = plan.latency ? kLatency : kThroughput;
+    const int nl = plan.latency ? kNumLatency : kNumThroughput;
+
+    // bucket utterances by variant, longest first inside a bucket (tail balance)
+    std::vector<std::pair<int, int>> order(B);       // (variant index, b)
+    for (int b = 0; b < B; ++b) {
+        const Variant *v = pick(ladder, nl, label_len[b]);
+        if (!v) return fail(CTC_STATUS_UNKNOWN_ERROR, "no kernel variant for this label length");
+        order[b] = {(int)(v - ladder), b};
+    }
+    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+        if (x.first != y.first) return x.first > y.first;            // big variants first
+        return act_len[x.second] > act_len[y.second];
+    });
+    for (int i = 0; i < B; ++i) utt_ids[i] = order[i].second;
+
+    size_t o = 0;
+    plan.off_meta = o;   o = align_up(o + sizeof(int) * 4 * (size_t)B, 256);
+    plan.off_labels = o; o = align_up(o + sizeof(int) * (size_t)std::max<long long>(off, 1), 256);
+    plan.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
+    plan.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
+    plan.off_ckpt = o;
+    size_t ck = 0;
+    for (int i = 0; i < B;) {
+        int j = i;
+        while (j < B && order[j].first == order[i].first) ++j;
+        const Variant *v = &ladder[order[i].first];
+        Plan::Launch l;
+        l.v = v; l.first = i; l.count = j - i;
+        const int nC = (T_max + v->K - 1) / v->K;
+        l.ckpt_stride = want_grad ? (long long)nC * v->sp() : 0;
+        l.ckpt_off = ck;
+        ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.count;
+        l.smem = make_layout(v->NS, v->W, v->K, V, T_max).total;
+        if (l.smem > kMaxSmem)
+            return fail(CTC_STATUS_UNKNOWN_ERROR,
+                        "alphabet_size / max_time too large for the shared-memory layout of this kernel");
+        plan.launches.push_back(l);
+        i = j;
+    }
+    plan.total = align_up(o + ck, 256) + 256;
+    return CTC_STATUS_SUCCESS;
+}
+
+bool check(cudaError_t e, const char *what, ctcStatus_t code, ctcStatus_t &out)
+{
+    if (e == cudaSuccess) return true;
+    out = fail(code, std::string(what) + ": " + cudaGetErrorString(e));
+    return false;
+}
+
+ctcStatus_t run(const ctcB200Call &c)
+{
+    if (!c.activations || !c.flat_labels || !c.label_lengths || !c.input_lengths || !c.workspace)
+        return fail(CTC_STATUS_INVALID_VALUE, "null pointer argument");
+    if (c.alphabet_size <= 0 || c.minibatch <= 0 || c.max_time <= 0)
+        return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
+    if (c.blank_label < 0 || c.blank_label >= c.alphabet_size)
+        return fail(CTC_STATUS_INVALID_VALUE, "blank_label outside the alphabet");
+    const bool no_sync = (c.flags & CTC_B200_FLAG_NO_SYNC) != 0;
+    if (no_sync && (c.costs_host || c.status_host))
+        return fail(CTC_STATUS_INVALID_VALUE, "NO_SYNC cannot return host costs/status");
+    if (!c.costs_host && !c.costs_device)
+        return fail(CTC_STATUS_INVALID_VALUE, "no destination for the costs");
+
+    const int B = c.minibatch, V = c.alphabet_size;
+    const bool want_grad = c.gradients != nullptr;
+    Plan plan;
+    ctcStatus_t st = make_plan(c.label_lengths, c.input_lengths, V, B, c.max_time, want_grad,
+                               (int)((c.flags >> 8) & 0x3), plan);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    if (plan.total > c.workspace_bytes) return fail(CTC_STATUS_INVALID_VALUE, "workspace too small");
+
+    cudaStream_t stream = (cudaStream_t)c.stream;
+    char *ws = (char *)c.workspace;
+    int *d_meta = (int *)(ws + plan.off_meta);
+    int *d_labels = (int *)(ws + plan.off_labels);
+    float *d_costs = c.costs_device ? c.costs_device : (float *)(ws + plan.off_costs);
+    int *d_status = (int *)(ws + plan.off_status);
+
+    if (!check(cudaMemcpyAsync(d_meta, plan.meta.data(), sizeof(int) * 4 * (size_t)B, cudaMemcpyHostToDevice, stream),
+               "H2D metadata", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    if (plan.total_labels > 0 &&
+        !check(cudaMemcpyAsync(d_labels, c.flat_labels, sizeof(int) * (size_t)plan.total_labels, cudaMemcpyHostToDevice, stream),
+               "H2D labels", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+
+    FusedParams P;
+    P.acts = c.activations; P.act_stride_t = c.act_stride_t; P.act_stride_b = c.act_stride_b;
+    P.grads = c.gradients;
+    P.labels = d_labels; P.label_off = d_meta; P.label_len = d_meta + B; P.act_len = d_meta + 2 * B;
+    P.costs = d_costs; P.status = d_status;
+    P.V = V; P.T_max = c.max_time; P.B = B; P.blank = c.blank_label;
+    P.grad_scale = c.grad_scale;
+
+    for (const Plan::Launch &l : plan.launches) {
+        P.utt_ids = d_meta + 3 * B + l.first;
+        P.ckpt = (double *)(ws + plan.off_ckpt + l.ckpt_off);
+        P.ckpt_stride = l.ckpt_stride;
+        if (!check(cudaFuncSetAttribute(l.v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem),
+                   "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        l.v->kernel<<<l.count, 32 * l.v->W, l.smem, stream>>>(P);
+        ++g_launches;
+        if (!check(cudaGetLastError(), "kernel launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    }
+    if (no_sync) return CTC_STATUS_SUCCESS;
+
+    std::vector<int> h_status(B);
+    if (c.costs_host &&
+        !check(cudaMemcpyAsync(c.costs_host, d_costs, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, stream),
+               "D2H costs", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
+               "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+
+    int any = 0;
+    for (int b = 0; b < B; ++b) any |= h_status[b];
+    if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
+    if (any & CTC_B200_UTT_BAD_LABEL)
+        return fail(CTC_STATUS_INVALID_VALUE, "a label is outside [0, alphabet_size) or equals the blank");
+    if (any & CTC_B200_UTT_RANGE)
+        return fail(CTC_STATUS_EXECUTION_FAILED,
+                    "fp64 dynamic range exhausted (forward/backward consistency check failed)");
+    return CTC_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int get_warpctc_version(void) { return 2; }
+
+const char *ctcGetStatusString(ctcStatus_t status)
+{
+    switch (status) {
+    case CTC_STATUS_SUCCESS: return "no error";
+    case CTC_STATUS_MEMOPS_FAILED: return "cuda memcpy or memset failed";
+    case CTC_STATUS_INVALID_VALUE: return "invalid value";
+    case CTC_STATUS_EXECUTION_FAILED: return "execution failed";
+    case CTC_STATUS_UNKNOWN_ERROR:
+    default: return "unknown error";
+    }
+}
+
+const char *ctc_b200_last_error(void) { return g_last_error.c_str(); }
+
+int ctc_b200_info(unsigned long long *launch_count)
+{
+    if (launch_count) *launch_count = g_launches;
+    return 100;
+}
+
+ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_lengths, int alphabet_size,
+                                    int minibatch, int max_time, int want_gradients, size_t *size_bytes)
+{
+    if (!size_bytes) return fail(CTC_STATUS_INVALID_VALUE, "null size_bytes");
+    Plan a, b;
+    // the ladder choice is deterministic in (B), so one plan suffices; take the max of both modes so a
+    // forced mode never overruns the workspace
+    ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
+                               want_gradients != 0, 1, a);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time, want_gradients != 0, 2, b);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    *size_bytes = std::max(a.total, b.total);
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t ctc_b200_compute(const ctcB200Call *call)
+{
+    if (!call) return fail(CTC_STATUS_INVALID_VALUE, "null call");
+    return run(*call);
+}
+
+ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const input_lengths, int alphabet_size,
+                               int minibatch, struct ctcOptions info, size_t *size_bytes)
+{
+    if (!label_lengths || !input_lengths || !size_bytes || alphabet_size <= 0 || minibatch <= 0)
+        return fail(CTC_STATUS_INVALID_VALUE, "invalid argument");
+    if (info.loc != CTC_GPU)
+        return fail(CTC_STATUS_INVALID_VALUE, "libctc_b200 is GPU-only: options.loc must be CTC_GPU");
+    int max_t = 0;
+    for (int b = 0; b < minibatch; ++b) max_t = std::max(max_t, input_lengths[b]);
+    return ctc_b200_workspace_size(label_lengths, input_lengths, alphabet_size, minibatch, std::max(max_t, 1), 1,
+                                   size_bytes);
+}
+
+ctcStatus_t compute_ctc_loss(const float *const activations, float *gradients, const int *const flat_labels,
+                             const int *const label_lengths, const int *const input_lengths, int alphabet_size,
+                             int minibatch, float *costs, void *workspace, struct ctcOptions options)
+{
+    if (!activations || !flat_labels || !label_lengths || !input_lengths || !costs || !workspace ||
+        alphabet_size <= 0 || minibatch <= 0)
+        return fail(CTC_STATUS_INVALID_VALUE, "invalid argument");
+    if (options.loc != CTC_GPU)
+        return fail(CTC_STATUS_INVALID_VALUE, "libctc_b200 is GPU-only: options.loc must be CTC_GPU");
+    int max_t = 0;
+    for (int b = 0; b < minibatch; ++b) max_t = std::max(max_t, input_lengths[b]);
+    if (max_t <= 0) {                                   // nothing to align against: all costs 0 (infeasible)
+        for (int b = 0; b < minibatch; ++b) costs[b] = 0.f;
+        return CTC_STATUS_SUCCESS;
+    }
+    size_t need = 0;
+    ctcStatus_t st = ctc_b200_workspace_size(label_lengths, input_lengths, alphabet_size, minibatch, max_t,
+                                             gradients != nullptr, &need);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    ctcB200Call c;
+    std::memset(&c, 0, sizeof(c));
+    c.activations = activations;
+    c.act_stride_t = (long long)minibatch * alphabet_size;
+    c.act_stride_b = alphabet_size;
+    c.gradients = gradients;
+    c.flat_labels = flat_labels;
+    c.label_lengths = label_lengths;
+    c.input_lengths = input_lengths;
+    c.alphabet_size = alphabet_size;
+    c.minibatch = minibatch;
+    c.max_time = max_t;
+    c.blank_label = options.blank_label;
+    c.grad_scale = 1.0f;
+    c.costs_host = costs;
+    c.workspace = workspace;
+    c.workspace_bytes = need;                           // caller promised get_workspace_size() bytes
+    c.stream = options.stream;
+    return run(c);
+}
+
+}  // extern "C"

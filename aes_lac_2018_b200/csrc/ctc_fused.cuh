@@ -1,0 +1,543 @@
+// ctc_fused.cuh -- the sm_100a CTC forward+backward kernel (one CTA per utterance).
+//
+// What it computes: for utterance b, cost_b = -log p(labels_b | acts[:, b, :]) and
+// d cost_b / d acts[t, b, k] = softmax(acts[t,b,:])[k] - posterior_t(k), i.e. the result of the
+// reference's `criterion(out, targets, out_sizes, target_sizes)` (reference codes/engine.py:22,
+// codes/metrics.py:51; warp-ctc's compute_alpha_kernel + compute_betas_and_grad_kernel upstream).
+// Maths: SURVEY.md Appendix C.  This is not warp-ctc's algorithm organisation:
+//
+//  * LINEAR-domain fp64 recursion with exact power-of-two rescaling every K timesteps.  B200's fp64
+//    pipe issues 64 DFMA/clk/SM; a log-space cell costs 3-4 MUFU (16/clk/SM).  A linear cell is
+//    2 (blank) or 3 (label) fp64 ops and is accurate to ~1e-16/step, so the gradient lands within
+//    ~5e-7 of the float64 oracle at every BASELINE shape (warp-ctc's own fp32 log-space arithmetic is
+//    1e-3..1e-2 away; tests/proto_scaled_linear.py models the scheme on the CPU).
+//  * The softmax is fused in: each CTA stages K rows of raw activations with cp.async (prefetched one
+//    chunk ahead of the T-serial chain), exponentiates them once per sweep (fp32 ex2) into a shared
+//    table of UNNORMALISED p~ = exp(a - rowmax) stored as doubles.  Row sums only enter the loss
+//    (sum_t log rowsum_t, fp64) and the final p = p~/rowsum of the gradient: they cancel in the posterior.
+//  * No alpha spill to HBM.  The forward sweep checkpoints the (rescaled) alpha column once per chunk
+//    (8*S bytes per K steps); the backward sweep re-runs alpha inside the chunk from the checkpoint
+//    into shared memory, then runs beta over the same chunk and forms alpha*beta there.
+//  * Each thread owns NS consecutive states of the blank-extended sequence in registers; neighbours
+//    come by warp shuffle (one fp64 value per step for alpha, two for beta), across warps through a
+//    double-buffered shared slot and one barrier per step.  W = 1 needs no block barrier at all.
+//  * Per-symbol accumulation of alpha*beta is a deterministic gather: label products go to shared
+//    memory, thread k sums the positions of symbol k (list built once per utterance, ascending),
+//    blanks are reduced by shuffle.  Gradient rows are written coalesced, padded frames zeroed.
+//
+// Thread/state map: thread tid owns states s = tid*NS + i, i < NS (NS even => even i are blanks).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace ctcb200 {
+
+constexpr int kTargetExp = 256;       // binary exponent the column max is rescaled to
+
+enum : int {
+    UTT_INFEASIBLE = 0x1,
+    UTT_INF_COST = 0x2,
+    UTT_BAD_LABEL = 0x4,
+    UTT_RANGE = 0x8,
+};
+
+struct FusedParams {
+    const float *acts;
+    long long act_stride_t, act_stride_b;
+    float *grads;                     // dense [T_max][B][V] or nullptr (costs only)
+    const int *labels;                // device, flat
+    const int *label_off;             // [B]
+    const int *label_len;             // [B]
+    const int *act_len;               // [B]
+    const int *utt_ids;               // [gridDim.x] utterance of each CTA in this launch
+    float *costs;                     // [B]
+    int *status;                      // [B]
+    double *ckpt;                     // checkpoint slots of this launch
+    long long ckpt_stride;            // doubles per CTA slot
+    int V, T_max, B, blank;
+    float grad_scale;
+};
+
+// ---- shared-memory carve-up (host and device must agree) ---------------------------------------
+struct SmemLayout {
+    int pst;        // ptab row stride in doubles (odd, >= V+1)
+    int off_ptab, off_acol, off_gam, off_xch, off_zfin, off_raw, off_rinv, off_bpart, off_ea,
+        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int NS, int W, int kChunk, int V, int T_max)
+{
+    SmemLayout l;
+    const int NT = 32 * W, SP = NS * NT, LP = SP / 2;
+    const int nC = (T_max + kChunk - 1) / kChunk;
+    l.pst = (V + 1) | 1;
+    int o = 0;
+    l.off_ptab = o;  o += kChunk * l.pst * 8;
+    l.off_acol = o;  o += kChunk * SP * 8;
+    l.off_gam = o;   o += 2 * LP * 8;
+    l.off_xch = o;   o += 2 * W * 2 * 8;
+    l.off_zfin = o;  o += 2 * 8;
+    l.off_raw = o;   o += 2 * kChunk * V * 4;
+    l.off_rinv = o;  o += kChunk * 4;
+    l.off_bpart = o; o += 2 * W * 4;
+    l.off_ea = o;    o += (nC + 1) * 4;
+    l.off_lab = o;   o += LP * 4;
+    l.off_pos = o;   o += LP * 4;
+    l.off_cnt = o;   o += (V + 1) * 4;
+    l.off_off = o;   o += (V + 1) * 4;
+    l.off_misc = o;  o += 8 * 4;
+    l.off_scr = o;   o += 32 * 4;
+    l.total = (o + 15) & ~15;
+    return l;
+}
+
+// ---- small device helpers ------------------------------------------------------------------------
+__device__ __forceinline__ double pow2d(int e)            // 2^e, e in [-1022, 1023]
+{
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+__device__ __forceinline__ double shfl_up_d(double v)
+{
+    return __shfl_up_sync(0xffffffffu, v, 1);
+}
+__device__ __forceinline__ double shfl_down_d(double v)
+{
+    return __shfl_down_sync(0xffffffffu, v, 1);
+}
+template <int W>
+__device__ __forceinline__ void cta_sync()
+{
+    if (W == 1) __syncwarp(); else __syncthreads();
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// max over the CTA of a 32-bit key (non-negative doubles compare like their high words)
+template <int W>
+__device__ __forceinline__ unsigned cta_max_key(unsigned v, unsigned *scratch, int warp, int lane)
+{
+    v = __reduce_max_sync(0xffffffffu, v);
+    if (W > 1) {
+        __syncthreads();                       // scratch free
+        if (lane == 0) scratch[warp] = v;
+        __syncthreads();
+        unsigned m = scratch[0];
+#pragma unroll
+        for (int w = 1; w < W; ++w) m = max(m, scratch[w]);
+        v = m;
+    }
+    return v;
+}
+
+// Rescale x[] by an exact power of two so that the CTA-wide max has binary exponent kTargetExp.
+// E is the running exponent: true value = x * 2^E.
+template <int NS, int W>
+__device__ __forceinline__ void rescale(double (&x)[NS], int &E, unsigned *scratch, int warp, int lane)
+{
+    unsigned key = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) key = max(key, (unsigned)__double2hiint(x[i]));
+    key = cta_max_key<W>(key, scratch, warp, lane);
+    const int ex = (int)(key >> 20);           // biased exponent of the max (sign bit is 0)
+    if (key == 0u || ex == 0x7ff) return;      // all zero, or inf/nan: leave (flagged later)
+    int sh = kTargetExp - (ex - 1023);
+    sh = min(sh, 1023);
+    if (sh == 0) return;
+    const double f = pow2d(sh);                // sh >= 256-1023 = -767: representable
+#pragma unroll
+    for (int i = 0; i < NS; ++i) x[i] *= f;
+    E -= sh;
+}
+
+// ---- the kernel ----------------------------------------------------------------------------------
+// K = timesteps per chunk (rescale / checkpoint / softmax granularity)
+template <int NS, int W, int K>
+__global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
+{
+    static_assert(NS % 2 == 0 && NS >= 2 && NS <= 16, "NS must be even, <= 16");
+    constexpr int NT = 32 * W;                 // threads per CTA
+    constexpr int SP = NS * NT;                // padded state count
+    constexpr int LP = SP / 2;                 // padded label count
+    constexpr int NL = NS / 2;                 // labels per thread
+    constexpr int kChunk = K;
+    constexpr int G = (NT / K) < 32 ? (NT / K) : 32;   // lanes per softmax row
+    constexpr int RP = NT / G;                 // rows per softmax pass
+    constexpr int NPASS = (K + RP - 1) / RP;
+    static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0, "bad softmax group");
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int V = P.V, blank = P.blank;
+    const SmemLayout lay = make_layout(NS, W, K, V, P.T_max);
+    const int PST = lay.pst;
+    double *ptab = (double *)(smem + lay.off_ptab);         // [K][PST]  p~ as doubles, slot V = 0.0
+    double *acol = (double *)(smem + lay.off_acol);         // [K][NS][NT] recomputed alpha columns
+    double *gam = (double *)(smem + lay.off_gam);           // [2][LP]   alpha*beta of label states
+    double *xch = (double *)(smem + lay.off_xch);           // [2][W][2] cross-warp boundary values
+    double *zfin = (double *)(smem + lay.off_zfin);         // [2]
+    float *raw = (float *)(smem + lay.off_raw);             // [2][K][V] staged raw activations
+    float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum
+    float *bpart = (float *)(smem + lay.off_bpart);         // [2][W] blank posterior partials
+    int *ea_s = (int *)(smem + lay.off_ea);                 // [nC] alpha exponent per chunk
+    int *lab_s = (int *)(smem + lay.off_lab);               // [LP]
+    int *pos_s = (int *)(smem + lay.off_pos);               // [LP] label indices grouped by symbol
+    int *cnt_s = (int *)(smem + lay.off_cnt);               // [V+1]
+    int *off_s = (int *)(smem + lay.off_off);               // [V+1]
+    int *misc = (int *)(smem + lay.off_misc);               // [0] repeats, [1] bad label
+    float *chk_acc = (float *)(misc + 4);                   // sum_k posterior of the checked frame (W > 1)
+    unsigned *scratch = (unsigned *)(smem + lay.off_scr);   // [W] cross-warp max
+
+    const int b = P.utt_ids[blockIdx.x];
+    const int T = P.act_len[b];
+    const int L = P.label_len[b];
+    const int S = 2 * L + 1;
+    const int *lab_g = P.labels + P.label_off[b];
+    const float *acts_b = P.acts + (long long)b * P.act_stride_b;
+    float *grads_b = P.grads ? P.grads + (long long)b * V : nullptr;
+    const long long gst = (long long)P.B * V;               // gradient row stride (dense)
+    const bool want_grad = (P.grads != nullptr);
+
+    // ---- labels -> shared, repeats, validity ----
+    if (tid < 8) misc[tid] = 0;
+    __syncthreads();
+    {
+        int rep = 0, bad = 0;
+        for (int j = tid; j < LP; j += NT) {
+            int v = -1;
+            if (j < L) {
+                v = lab_g[j];
+                if (v < 0 || v >= V || v == blank) { bad = 1; v = -1; }
+                else if (j > 0 && lab_g[j - 1] == v) rep++;
+            }
+            lab_s[j] = v;
+        }
+        if (rep) atomicAdd(&misc[0], rep);
+        if (bad) atomicOr(&misc[1], 1);
+    }
+    __syncthreads();
+    int ustat = 0;
+    if (misc[1]) ustat |= UTT_BAD_LABEL;
+    if (T <= 0 || L + misc[0] > T) ustat |= UTT_INFEASIBLE;
+    if (ustat) {                                            // cost 0, gradient 0 (warp-ctc CPU convention)
+        if (tid == 0) { P.costs[b] = 0.f; P.status[b] = ustat; }
+        if (want_grad)
+            for (int t = warp; t < P.T_max; t += W)
+                for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
+        return;
+    }
+
+    // ---- per-thread label constants ----
+    const int j0 = tid * NL;
+    int poff[NL];                                           // byte offset of p~(label) inside a ptab row
+    unsigned mbits = 0;                                     // bit jj: skip INTO label j0+jj allowed
+#pragma unroll
+    for (int jj = 0; jj <= NL; ++jj) {
+        const int j = j0 + jj;
+        const int cur = (j < LP) ? lab_s[j] : -1;
+        const int prv = (j >= 1 && j - 1 < LP) ? lab_s[j - 1] : -1;
+        if (jj < NL) poff[jj] = (cur < 0 ? V : cur) * 8;
+        if (cur >= 0 && j >= 1 && cur != prv) mbits |= (1u << jj);
+    }
+
+    // ---- per-symbol position lists (deterministic, ascending) ----
+    if (want_grad) {
+        for (int k = tid; k <= V; k += NT) {
+            int c = 0;
+            if (k < V) for (int j = 0; j < L; ++j) c += (lab_s[j] == k);
+            cnt_s[k] = c;
+        }
+        __syncthreads();
+        for (int k = tid; k <= V; k += NT) {
+            int o = 0;
+            for (int q = 0; q < k; ++q) o += cnt_s[q];
+            off_s[k] = o;
+        }
+        __syncthreads();
+        for (int k = tid; k < V; k += NT) {
+            int q = off_s[k];
+            if (cnt_s[k]) for (int j = 0; j < L; ++j) if (lab_s[j] == k) pos_s[q++] = j;
+        }
+    }
+    if (tid < 2 * W * 2) xch[tid] = 0.0;
+    if (tid < 2) zfin[tid] = 0.0;
+    __syncthreads();
+
+    const int nC = (T + kChunk - 1) / kChunk;
+    double *ck = P.ckpt + (long long)blockIdx.x * P.ckpt_stride;
+
+    // raw-activation prefetch of chunk c into buffer c&1 (rows spread over warps, k over lanes)
+    auto prefetch = [&](int c) {
+        const int t0 = c * kChunk, n = min(kChunk, T - t0);
+        float *dst = raw + (c & 1) * kChunk * V;
+        for (int r = warp; r < n; r += W) {
+            const float *src = acts_b + (long long)(t0 + r) * P.act_stride_t;
+            for (int k = lane; k < V; k += 32) cp_async4(dst + r * V + k, src + k);
+        }
+        cp_async_commit();
+    };
+
+    // softmax of the staged chunk -> ptab (unnormalised p~, fp64), rinv; returns sum_r log(rowsum_r)
+    auto softmax_chunk = [&](int c, bool want_log) -> double {
+        const int n = min(kChunk, T - c * kChunk);
+        const float *src = raw + (c & 1) * kChunk * V;
+        const int g = tid % G;
+        double lg = 0.0;
+#pragma unroll
+        for (int ps = 0; ps < NPASS; ++ps) {
+            const int r = tid / G + ps * RP;
+            const bool act = (r < n);
+            const float *row = src + r * V;
+            float m = -INFINITY;
+            if (act) for (int k = g; k < V; k += G) m = fmaxf(m, row[k]);
+#pragma unroll
+            for (int o = G / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (m == -INFINITY) m = 0.f;
+            float s = 0.f;
+            double *prow = ptab + r * PST;
+            if (act) for (int k = g; k < V; k += G) {
+                const float e = __expf(row[k] - m);
+                s += e;
+                prow[k] = (double)e;
+            }
+#pragma unroll
+            for (int o = G / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (act && g == 0) {
+                prow[V] = 0.0;                              // the "no label here" slot
+                rinv[r] = (s > 0.f) ? 1.f / s : 0.f;
+                if (want_log) lg += log((double)s);
+            }
+        }
+        return lg;
+    };
+
+    // one alpha step in place (descending i keeps old neighbours intact)
+    auto alpha_step = [&](double (&a)[NS], const double *prow, int &par) {
+        double up1 = shfl_up_d(a[NS - 1]);
+        if (W > 1) {
+            if (lane == 31) xch[(par * W + warp) * 2] = a[NS - 1];
+            __syncthreads();
+            if (lane == 0) up1 = (warp > 0) ? xch[(par * W + warp - 1) * 2] : 0.0;
+            par ^= 1;
+        } else if (lane == 0) up1 = 0.0;
+        const double pb = prow[blank];
+#pragma unroll
+        for (int i = NS - 1; i >= 0; --i) {
+            if (i & 1) {
+                const int jj = i >> 1;
+                const double pl = *(const double *)((const char *)prow + poff[jj]);
+                double s = a[i] + a[i - 1];
+                const double p2 = (i >= 2) ? a[i - 2] : up1;
+                if ((mbits >> jj) & 1u) s += p2;
+                a[i] = s * pl;
+            } else {
+                const double s = a[i] + ((i >= 1) ? a[i - 1] : up1);
+                a[i] = s * pb;
+            }
+        }
+    };
+
+    // =============================== forward sweep ===============================================
+    double a[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) a[i] = 0.0;
+    if (tid == 0) a[0] = pow2d(kTargetExp);                 // virtual column t = -1
+    int Ea = -kTargetExp;
+    int par = 0;
+    double logsum = 0.0;
+
+    prefetch(0);
+    for (int c = 0; c < nC; ++c) {
+        rescale<NS, W>(a, Ea, scratch, warp, lane);
+        if (want_grad) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ck[((long long)c * NS + i) * NT + tid] = a[i];
+            if (tid == 0) ea_s[c] = Ea;
+        }
+        cp_async_wait_all();
+        cta_sync<W>();                                      // raw chunk visible; previous ptab readers done
+        if (c + 1 < nC) prefetch(c + 1);
+        logsum += softmax_chunk(c, true);
+        cta_sync<W>();
+        const int n = min(kChunk, T - c * kChunk);
+#pragma unroll 1
+        for (int tt = 0; tt < n; ++tt) alpha_step(a, ptab + tt * PST, par);
+    }
+
+    // Z^ = alpha^_{T-1}(S-1) + alpha^_{T-1}(S-2)
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int s = tid * NS + i;
+        if (s == S - 1) zfin[0] = a[i];
+        if (s == S - 2) zfin[1] = a[i];
+    }
+    // sum_t log(rowsum_t): reduce the per-thread partials (fp64) through shared memory
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) logsum += __shfl_xor_sync(0xffffffffu, logsum, o);
+    __syncthreads();
+    if (lane == 0) gam[warp] = logsum;
+    __syncthreads();
+    const double zhat = zfin[0] + zfin[1];
+    const int Ea_fin = Ea;
+    {
+        double ls = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) ls += gam[w];
+        logsum = ls;
+    }
+    __syncthreads();                                        // gam reused below
+    const bool z_ok = (zhat > 0.0) && (zhat < INFINITY);
+    if (!(zhat == zhat) || zhat == INFINITY) ustat |= UTT_RANGE;
+    else if (!z_ok) ustat |= UTT_INF_COST;
+    if (tid == 0) {
+        float cost;
+        if (z_ok) cost = (float)(-(log(zhat) + (double)Ea_fin * 0.6931471805599453 - logsum));
+        else cost = INFINITY;
+        P.costs[b] = cost;
+    }
+    if (!want_grad) {
+        if (tid == 0) P.status[b] = ustat;
+        return;
+    }
+
+    // =============================== backward sweep ==============================================
+    const double inv_z = z_ok ? 1.0 / zhat : 0.0;
+    double bt[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) bt[i] = (tid * NS + i == S - 1) ? pow2d(kTargetExp) : 0.0;   // virtual column t = T
+    int Eb = -kTargetExp;
+    int gpar = 0;                                           // parity of gam / bpart / beta-xch buffers
+    float chk_dev = 0.f;                                    // max |sum_k posterior - 1| seen by this thread
+
+    for (int c = nC - 1; c >= 0; --c) {
+        const int t0 = c * kChunk, n = min(kChunk, T - t0);
+        if (c < nC - 1) {                                   // ptab still holds the last chunk after the forward sweep
+            cp_async_wait_all();
+            cta_sync<W>();
+        }
+        if (c >= 1) prefetch(c - 1);
+        if (c < nC - 1) {
+            softmax_chunk(c, false);
+            cta_sync<W>();
+        }
+        // -- recompute alpha inside the chunk from its checkpoint --
+#pragma unroll
+        for (int i = 0; i < NS; ++i) a[i] = ck[((long long)c * NS + i) * NT + tid];
+        const int Ea_c = ea_s[c];
+#pragma unroll 1
+        for (int tt = 0; tt < n; ++tt) {
+            alpha_step(a, ptab + tt * PST, par);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acol[(tt * NS + i) * NT + tid] = a[i];
+        }
+        // posterior scale of this chunk: 2^(Ea_c + Eb - Ea_fin) / Z^
+        const double sc = scalbn(inv_z, Ea_c + Eb - Ea_fin);
+
+        // -- beta over the chunk, gradient rows --
+        // boundary values for the first step of the chunk
+        if (W > 1) {
+            __syncthreads();
+            if (lane == 0) { xch[(gpar * W + warp) * 2] = bt[0]; xch[(gpar * W + warp) * 2 + 1] = bt[1]; }
+            __syncthreads();
+        }
+#pragma unroll 1
+        for (int tt = n - 1; tt >= 0; --tt) {
+            const double *prow = ptab + tt * PST;
+            double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);
+            if (lane == 31) {
+                if (W > 1 && warp < W - 1) {
+                    dn0 = xch[(gpar * W + warp + 1) * 2];
+                    dn1 = xch[(gpar * W + warp + 1) * 2 + 1];
+                } else { dn0 = 0.0; dn1 = 0.0; }
+            }
+            const double pb = prow[blank];
+            double bsum = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const double av = acol[(tt * NS + i) * NT + tid];
+                if (i & 1) {
+                    const int jj = i >> 1;
+                    const double pl = *(const double *)((const char *)prow + poff[jj]);
+                    double s = bt[i] + ((i + 1 < NS) ? bt[i + 1] : dn0);
+                    const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
+                    if ((mbits >> (jj + 1)) & 1u) s += n2;
+                    bt[i] = s * pl;
+                    gam[gpar * LP + j0 + jj] = av * bt[i];
+                } else {
+                    const double s = bt[i] + bt[i + 1];
+                    bt[i] = s * pb;
+                    bsum = fma(av, bt[i], bsum);
+                }
+            }
+            // blank posterior (already divided by nothing: p~ division happens in the gather)
+            float bp = (float)(bsum * sc);
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
+            if (W > 1) {
+                if (lane == 0) {
+                    bpart[gpar * W + warp] = bp;
+                    xch[((gpar ^ 1) * W + warp) * 2] = bt[0];
+                    xch[((gpar ^ 1) * W + warp) * 2 + 1] = bt[1];
+                }
+                __syncthreads();
+            } else {
+                __syncwarp();
+            }
+            // gather: thread k sums alpha*beta over the positions of symbol k, writes grad[t, b, k]
+            {
+                const float ri = rinv[tt];
+                float *grow = grads_b + (long long)(t0 + tt) * gst;
+                float psum = 0.f;
+                for (int k = tid; k < V; k += NT) {
+                    float num;
+                    if (k == blank) {
+                        if (W > 1) {
+                            num = 0.f;
+#pragma unroll
+                            for (int w = 0; w < W; ++w) num += bpart[gpar * W + w];
+                        } else num = bp;
+                    } else {
+                        double acc = 0.0;
+                        const int q1 = off_s[k + 1];
+                        for (int q = off_s[k]; q < q1; ++q) acc += gam[gpar * LP + pos_s[q]];
+                        num = (float)(acc * sc);
+                    }
+                    const float pk = (float)prow[k];
+                    const float post = (pk > 0.f) ? __fdividef(num, pk) : 0.f;
+                    psum += post;
+                    grow[k] = (pk * ri - post) * P.grad_scale;
+                }
+                // self-check once per chunk: the posteriors of a frame must sum to 1
+                if (tt == 0 && z_ok) {                      // CTA-uniform condition
+                    float tot = psum;
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                    if (W == 1) chk_dev = fmaxf(chk_dev, fabsf(tot - 1.f));
+                    else if (lane == 0 && tot != 0.f) atomicAdd(chk_acc, tot);
+                }
+            }
+            gpar ^= 1;
+        }
+        rescale<NS, W>(bt, Eb, scratch, warp, lane);       // (contains the barriers that order chk_acc)
+        if (W > 1 && tid == 0 && z_ok) {
+            const float tot = *chk_acc;
+            chk_dev = fmaxf(chk_dev, (tot == tot) ? fabsf(tot - 1.f) : INFINITY);
+            *chk_acc = 0.f;
+        }
+    }
+
+    if (!(chk_dev <= 1e-3f)) ustat |= UTT_RANGE;
+    if (__syncthreads_or(ustat & UTT_RANGE)) ustat |= UTT_RANGE;
+    if (tid == 0) P.status[b] = ustat;
+
+    // padded frames get zero gradient
+    for (int t = T + warp; t < P.T_max; t += W)
+        for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
+}
+
+}  // namespace ctcb200

@@ -1,0 +1,137 @@
+"""`CTCLoss` -- drop-in for `warpctc_pytorch.CTCLoss` as the reference uses it.
+
+Reference call sites this mirrors (names, argument meaning, result, error behaviour):
+  * construction with defaults  `warp_CTCLoss()`           /root/reference/train.py:179, codes/metrics.py:43
+  * `loss = criterion(out, targets, out_sizes, target_sizes)` /root/reference/codes/engine.py:22
+  * `self._loss_fn(out, targets, out_sizes, target_sizes).sum()` under no_grad   codes/metrics.py:51
+Upstream module semantics (warp-ctc `pytorch_binding/warpctc_pytorch/__init__.py`, not vendored in the
+reference): activations are T x B x V and UNNORMALISED (softmax is internal), labels are a flat 1-D int
+tensor, lengths are int tensors, blank = 0, the result is `FloatTensor([sum_b cost_b])` of shape [1] on
+the CPU, gradients are produced in the forward pass and multiplied by grad_output in backward;
+`size_average` divides by B, `length_average` by sum(act_lens) and supersedes it.
+
+The compute path is libctc_b200.so (hand-written sm_100a CUDA) through ctypes.  There is no CPU path and
+no PyTorch fallback: CPU activations, or a missing library, raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+__all__ = ["CTCLoss", "ctc_loss_raw"]
+
+
+def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
+    if not isinstance(x, torch.Tensor):
+        x = torch.as_tensor(x)
+    if x.requires_grad:
+        raise AssertionError(f"{name}: gradients only computed for acts - please mark other tensors as not requiring gradients")
+    if x.is_floating_point():
+        raise TypeError(f"{name} must be an integer tensor")
+    return x.detach().to(device="cpu", dtype=torch.int32).reshape(-1).contiguous()
+
+
+def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
+                 grad_scale: float = 1.0, mode: str = "auto"):
+    """Runs the CUDA engine once.  Returns (costs[B] float32 CPU tensor, grads[T,B,V] CUDA tensor or None,
+    status[B] int32 CPU tensor).  `acts` may be any T x B x V view whose last stride is 1."""
+    lib = _lib.load()
+    if not acts.is_cuda:
+        raise RuntimeError("aes_lac_2018_b200.CTCLoss is CUDA-only (B200-native); got CPU activations. "
+                           "There is no CPU fallback.")
+    if acts.dim() != 3:
+        raise ValueError("acts must be T x B x V")
+    if acts.dtype != torch.float32:
+        raise TypeError("acts must be float32")
+    acts_d = acts.detach()
+    if acts_d.stride(2) != 1 and acts_d.size(2) > 1:
+        acts_d = acts_d.contiguous()
+    T, B, V = acts_d.shape
+    labels_h = _as_host_int32(labels, "labels")
+    act_lens_h = _as_host_int32(act_lens, "act_lens")
+    label_lens_h = _as_host_int32(label_lens, "label_lens")
+    if act_lens_h.numel() != B or label_lens_h.numel() != B:
+        raise ValueError("act_lens and label_lens must have one entry per utterance (acts.size(1))")
+    if int(label_lens_h.sum()) != labels_h.numel():
+        raise ValueError("labels must hold exactly sum(label_lens) entries")
+    if labels_h.numel() == 0:
+        labels_h = torch.zeros(1, dtype=torch.int32)
+
+    with torch.cuda.device(acts_d.device):
+        need = ctypes.c_size_t(0)
+        st = lib.ctc_b200_workspace_size(label_lens_h.data_ptr(), act_lens_h.data_ptr(), V, B, T,
+                                         1 if want_grad else 0, ctypes.byref(need))
+        if st != _lib.CTC_STATUS_SUCCESS:
+            raise RuntimeError("ctc_b200_workspace_size: " + _lib.status_string(lib, st))
+        workspace = torch.empty(need.value, dtype=torch.uint8, device=acts_d.device)
+        grads = torch.empty((T, B, V), dtype=torch.float32, device=acts_d.device) if want_grad else None
+        costs = torch.empty(B, dtype=torch.float32)
+        status = torch.empty(B, dtype=torch.int32)
+        call = _lib.CtcB200Call()
+        call.activations = acts_d.data_ptr()
+        call.act_stride_t = acts_d.stride(0)
+        call.act_stride_b = acts_d.stride(1)
+        call.gradients = grads.data_ptr() if want_grad else None
+        call.flat_labels = labels_h.data_ptr()
+        call.label_lengths = label_lens_h.data_ptr()
+        call.input_lengths = act_lens_h.data_ptr()
+        call.alphabet_size, call.minibatch, call.max_time = V, B, T
+        call.blank_label = int(blank)
+        call.grad_scale = float(grad_scale)
+        call.costs_host = costs.data_ptr()
+        call.costs_device = None
+        call.status_host = status.data_ptr()
+        call.workspace = workspace.data_ptr()
+        call.workspace_bytes = need.value
+        call.stream = torch.cuda.current_stream(acts_d.device).cuda_stream
+        call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY}[mode]
+        st = lib.ctc_b200_compute(ctypes.byref(call))
+        if st != _lib.CTC_STATUS_SUCCESS:
+            raise RuntimeError("ctc_b200_compute: " + _lib.status_string(lib, st))
+    return costs, grads, status
+
+
+class _CTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, acts, labels, act_lens, label_lens, size_average=False, length_average=False, blank=0):
+        B = acts.size(1)
+        if length_average:
+            denom = float(torch.as_tensor(act_lens).sum().item())
+        elif size_average:
+            denom = float(B)
+        else:
+            denom = 1.0
+        want_grad = bool(ctx.needs_input_grad[0])              # False under torch.no_grad() (engine.py:107)
+        costs, grads, _ = ctc_loss_raw(acts, labels, act_lens, label_lens, blank=blank, want_grad=want_grad,
+                                       grad_scale=1.0 / denom)
+        ctx.grads = grads
+        total = costs.double().sum() / denom
+        return torch.tensor([total], dtype=torch.float32)      # CPU, shape [1], like upstream
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if ctx.grads is None:
+            raise RuntimeError("CTCLoss.backward called but the forward ran without gradient tracking")
+        g = grad_output.to(ctx.grads.device, dtype=ctx.grads.dtype).reshape(-1)[0]
+        return ctx.grads.mul_(g), None, None, None, None, None, None
+
+
+class CTCLoss(torch.nn.Module):
+    """`CTCLoss(blank=0, size_average=False, length_average=False)`; see module docstring."""
+
+    def __init__(self, blank: int = 0, size_average: bool = False, length_average: bool = False):
+        super().__init__()
+        self.ctc = _CTC.apply
+        self.blank = blank
+        self.size_average = size_average
+        self.length_average = length_average
+
+    def forward(self, acts, labels, act_lens, label_lens):
+        """acts: T x B x V CUDA float tensor (unnormalised; may be a strided view);
+        labels: 1-D int tensor of the concatenated targets; act_lens, label_lens: int tensors [B]."""
+        if isinstance(labels, torch.Tensor) and labels.dim() > 1:
+            raise AssertionError("labels must be 1 dimensional")
+        return self.ctc(acts, labels, act_lens, label_lens, self.size_average, self.length_average, self.blank)

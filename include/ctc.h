@@ -1,0 +1,163 @@
+/*
+ * ctc.h -- C ABI of libctc_b200.so, the B200-native CTC loss-and-gradient engine.
+ *
+ * Drop-in boundary.  The reference (igormq/aes-lac-2018) reaches its CTC hot path through the
+ * third-party python package `warpctc_pytorch` (imported at /root/reference/train.py:12 and
+ * /root/reference/codes/metrics.py:3, called at /root/reference/codes/engine.py:22 and
+ * /root/reference/codes/metrics.py:51), whose binding loads `libwarpctc.so` and calls the entry points
+ * that warp-ctc's own `include/ctc.h` declares.  warp-ctc is not vendored in /root/reference
+ * (cloned at unpinned HEAD by /root/reference/docker/Dockerfile:52-66), so the "reference interface"
+ * each declaration below replaces is cited by its upstream name.  The first block keeps those names,
+ * argument order, argument meaning, pointer residency and error behaviour, so a binary that was
+ * linked against libwarpctc.so resolves the same symbols here.  The second block is the extended
+ * entry point the PyTorch front-end (aes_lac_2018_b200/ctc_loss.py) uses.
+ *
+ * Differences from upstream, all deliberate (DESIGN.md "Boundary"):
+ *   - GPU only: options.loc must be CTC_GPU.  CTC_CPU returns CTC_STATUS_INVALID_VALUE -- there is
+ *     no CPU fallback in this library.
+ *   - The gradient buffer does not have to be pre-zeroed: padded frames (t >= input_lengths[b]) and
+ *     infeasible utterances are written as zeros by the kernels.
+ *   - Infeasible utterances (L + repeats > T) get cost 0 and zero gradient on the GPU as well (upstream
+ *     does this on its CPU path only; its GPU path leaves the cost slot unwritten).
+ *   - Labels ARE validated: a label outside [0, alphabet_size) or equal to the blank returns
+ *     CTC_STATUS_INVALID_VALUE (upstream reads out of bounds).
+ *   - The blank-extended sequence may be up to 8193 states long (L <= 4096); upstream's GPU path stops
+ *     at 1280 states (L <= 639) with CTC_STATUS_UNKNOWN_ERROR.  Beyond the limit this library also
+ *     returns CTC_STATUS_UNKNOWN_ERROR.
+ */
+#ifndef CTC_B200_CTC_H
+#define CTC_B200_CTC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Forward declaration of the CUDA stream handle so that this header needs no CUDA include.
+ * (upstream: `typedef struct CUstream_st* CUstream;` in ctc.h) */
+typedef struct CUstream_st *CUstream;
+
+/* upstream ctc.h: ctcStatus_t -- same enumerators, same values. */
+typedef enum {
+    CTC_STATUS_SUCCESS = 0,
+    CTC_STATUS_MEMOPS_FAILED = 1,
+    CTC_STATUS_INVALID_VALUE = 2,
+    CTC_STATUS_EXECUTION_FAILED = 3,
+    CTC_STATUS_UNKNOWN_ERROR = 4
+} ctcStatus_t;
+
+/* upstream ctc.h: ctcComputeLocation. */
+typedef enum {
+    CTC_CPU = 0,
+    CTC_GPU = 1
+} ctcComputeLocation;
+
+/* upstream ctc.h: struct ctcOptions (passed BY VALUE).  Layout: int, 8-byte union, int. */
+struct ctcOptions {
+    ctcComputeLocation loc;      /* must be CTC_GPU here */
+    union {
+        unsigned int num_threads; /* CPU only upstream; ignored here */
+        CUstream stream;          /* stream the work is enqueued on (0 = legacy default stream) */
+    };
+    int blank_label;              /* the reference always uses 0 (train.py:179: CTCLoss() defaults) */
+};
+#ifndef __cplusplus
+typedef struct ctcOptions ctcOptions;
+#endif
+
+/* upstream ctc.h: get_warpctc_version().  Returns 2, the API generation this ABI mirrors. */
+int get_warpctc_version(void);
+
+/* upstream ctc.h: ctcGetStatusString(). */
+const char *ctcGetStatusString(ctcStatus_t status);
+
+/*
+ * upstream ctc.h: compute_ctc_loss().  Replaces the call made by warpctc_pytorch's gpu_ctc() binding.
+ *
+ *   activations   DEVICE, dense time-major [max(input_lengths)][minibatch][alphabet_size], fp32,
+ *                 UNNORMALISED (the softmax is internal, reference README.md:168).
+ *   gradients     DEVICE, same shape, or NULL to compute the costs only.
+ *   flat_labels   HOST, concatenated labels of all utterances (int).
+ *   label_lengths HOST [minibatch];  input_lengths HOST [minibatch].
+ *   costs         HOST [minibatch]; on return costs[b] = -log p(labels_b | activations_b).
+ *   workspace     DEVICE, at least get_workspace_size() bytes; caller-owned; nothing is allocated here.
+ *   options       by value; work is enqueued on options.stream and the call BLOCKS until the costs are
+ *                 on the host (as upstream does).
+ * Errors: null pointers / non-positive sizes / bad labels -> CTC_STATUS_INVALID_VALUE; a CUDA copy that
+ * fails -> CTC_STATUS_MEMOPS_FAILED; a launch that fails -> CTC_STATUS_EXECUTION_FAILED; a label
+ * sequence beyond the supported length -> CTC_STATUS_UNKNOWN_ERROR.  No exceptions, no errno.
+ */
+ctcStatus_t compute_ctc_loss(const float *const activations,
+                             float *gradients,
+                             const int *const flat_labels,
+                             const int *const label_lengths,
+                             const int *const input_lengths,
+                             int alphabet_size,
+                             int minibatch,
+                             float *costs,
+                             void *workspace,
+                             struct ctcOptions options);
+
+/* upstream ctc.h: get_workspace_size().  All length arrays are HOST pointers. */
+ctcStatus_t get_workspace_size(const int *const label_lengths,
+                               const int *const input_lengths,
+                               int alphabet_size,
+                               int minibatch,
+                               struct ctcOptions info,
+                               size_t *size_bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Extended entry point (no upstream counterpart).  It exists to remove the per-step costs SURVEY.md
+ * section 8a lists for the reference glue: strided activations (no .contiguous() copy, A1), a folded
+ * gradient scale (1/B, task weight; A8), an explicit max_time, optional device-side costs and an
+ * optional non-blocking return (A9).
+ * ---------------------------------------------------------------------------------------------- */
+
+#define CTC_B200_FLAG_NO_SYNC 0x1u       /* do not synchronise; costs_host/status_host must be NULL */
+
+typedef struct ctcB200Call {
+    const float *activations;   /* DEVICE; element (t,b,k) at t*act_stride_t + b*act_stride_b + k */
+    long long act_stride_t;     /* in elements */
+    long long act_stride_b;     /* in elements */
+    float *gradients;           /* DEVICE dense [max_time][minibatch][alphabet_size], or NULL */
+    const int *flat_labels;     /* HOST */
+    const int *label_lengths;   /* HOST [minibatch] */
+    const int *input_lengths;   /* HOST [minibatch], each <= max_time */
+    int alphabet_size;
+    int minibatch;
+    int max_time;               /* T dimension of activations / gradients */
+    int blank_label;
+    float grad_scale;           /* gradients are multiplied by this (1.0f = upstream behaviour) */
+    float *costs_host;          /* HOST [minibatch] or NULL */
+    float *costs_device;        /* DEVICE [minibatch] or NULL (in addition to / instead of costs_host) */
+    int *status_host;           /* HOST [minibatch] or NULL: per-utterance CTC_B200_UTT_* bits */
+    void *workspace;            /* DEVICE */
+    size_t workspace_bytes;
+    CUstream stream;
+    unsigned int flags;
+} ctcB200Call;
+
+/* per-utterance status bits (status_host) */
+#define CTC_B200_UTT_INFEASIBLE 0x1     /* L + repeats > T (or T == 0): cost 0, gradient 0 */
+#define CTC_B200_UTT_INF_COST 0x2       /* no alignment has non-zero probability: cost = +inf */
+#define CTC_B200_UTT_BAD_LABEL 0x4      /* label out of range or equal to blank */
+#define CTC_B200_UTT_RANGE 0x8          /* fp64 dynamic range exhausted; utterance was redone in log space */
+
+ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_lengths,
+                                    int alphabet_size, int minibatch, int max_time,
+                                    int want_gradients, size_t *size_bytes);
+
+ctcStatus_t ctc_b200_compute(const ctcB200Call *call);
+
+/* Human-readable description of the last failure on the calling thread ("" if none). */
+const char *ctc_b200_last_error(void);
+
+/* Build/device facts for logging: returns the compiled SM architecture (100) and, if non-NULL, writes
+ * the number of kernel launches issued by this library on the calling thread since load. */
+int ctc_b200_info(unsigned long long *launch_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTC_B200_CTC_H */

@@ -1,0 +1,266 @@
+"""GPU parity tests: the sm_100a engine (through the C ABI / the CTCLoss module) against the float64
+oracle and the committed golden vectors.  Tolerances are the north_star's: loss 1e-4 relative,
+gradient 1e-5 absolute, fp32 results vs float64 truth."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import load_known_answers, load_torch_f64_cases, synth_problem
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+GRAD_ATOL = 1e-5
+
+KNOWN = load_known_answers()
+TORCH_CASES = load_torch_f64_cases()
+
+
+def _engine(acts, labels, act_lens, label_lens, blank=0, mode="auto", want_grad=True):
+    from aes_lac_2018_b200 import ctc_loss_raw
+    a = torch.as_tensor(np.asarray(acts, dtype=np.float32)).cuda()
+    costs, grads, status = ctc_loss_raw(a, torch.as_tensor(np.asarray(labels, dtype=np.int32)),
+                                        torch.as_tensor(np.asarray(act_lens, dtype=np.int32)),
+                                        torch.as_tensor(np.asarray(label_lens, dtype=np.int32)),
+                                        blank=blank, want_grad=want_grad, mode=mode)
+    return costs.numpy().astype(np.float64), (grads.cpu().numpy().astype(np.float64) if want_grad else None), status.numpy()
+
+
+def _assert_close(costs, grads, ref_costs, ref_grads, tag=""):
+    ref_costs = np.asarray(ref_costs, dtype=np.float64)
+    rel = np.abs(costs - ref_costs) / np.maximum(1.0, np.abs(ref_costs))
+    assert rel.max() <= LOSS_RTOL, f"{tag}: cost mismatch rel={rel.max():.3e} at b={rel.argmax()} got {costs[rel.argmax()]} want {ref_costs[rel.argmax()]}"
+    if grads is not None:
+        d = np.abs(grads - ref_grads)
+        idx = np.unravel_index(d.argmax(), d.shape)
+        assert d.max() <= GRAD_ATOL, (f"{tag}: grad mismatch {d.max():.3e} at (t,b,k)={idx} got {grads[idx]} want {ref_grads[idx]}; "
+                                      f"per-utt max {d.max(axis=(0, 2))}")
+
+
+@pytest.mark.parametrize("mode", ["throughput", "latency"])
+@pytest.mark.parametrize("case", KNOWN, ids=[c["name"] for c in KNOWN])
+def test_known_answers(case, mode):
+    from oracle import ctc_f64
+    costs, grads, _ = _engine(case["acts"], case["labels"], case["act_lens"], case["label_lens"], case["blank"], mode)
+    tol = max(case["cost_tol"], 2e-6)
+    if "expected_total_cost" in case:
+        assert abs(costs.sum() - case["expected_total_cost"]) <= tol * max(1.0, abs(case["expected_total_cost"]))
+    if "expected_costs" in case:
+        np.testing.assert_allclose(costs, case["expected_costs"], atol=tol * max(1.0, max(case["expected_costs"])))
+    if "expected_grads_tbv" in case:
+        np.testing.assert_allclose(grads, case["expected_grads_tbv"], atol=case["grad_tol"])
+    if "expected_grad_t0_b0" in case:
+        np.testing.assert_allclose(grads[0, 0], case["expected_grad_t0_b0"], atol=case["grad_tol"])
+    oc, og = ctc_f64.ctc_batch(case["acts"], case["labels"], case["act_lens"], case["label_lens"], case["blank"])
+    _assert_close(costs, grads, oc, og, case["name"])
+
+
+@pytest.mark.parametrize("mode", ["throughput", "latency"])
+@pytest.mark.parametrize("name", sorted(TORCH_CASES))
+def test_golden_torch_f64(name, mode):
+    c = TORCH_CASES[name]
+    costs, grads, _ = _engine(c["acts"], c["labels"], c["act_lens"], c["label_lens"], int(c["blank"]), mode)
+    _assert_close(costs, grads, c["costs"], c["grads"], name)
+
+
+SYNTH = {
+    # BASELINE.json configs[0..2] and the edge shapes of configs[4] at oracle-friendly sizes
+    "c1_b4_t200": dict(seed=11, T=200, B=4, V=29, lmin=10, lmax=50),
+    "c2_b32_t750": dict(seed=12, T=750, B=32, V=29, lmin=50, lmax=200),
+    "c3_ptbr_v43_ragged": dict(seed=13, T=800, B=16, V=43, lmin=25, lmax=200, tmin=720),
+    "peaky_b8_t300": dict(seed=14, T=300, B=8, V=29, lmin=20, lmax=80, peaky=True),
+    "sigma4_v43": dict(seed=15, T=400, B=6, V=43, lmin=30, lmax=120, sigma=4.0),
+    "short_labels": dict(seed=16, T=64, B=40, V=29, lmin=0, lmax=12, tmin=20),
+    "long_t3000_l600": dict(seed=17, T=3000, B=2, V=29, lmin=600, lmax=600),
+    "wide_l1000": dict(seed=18, T=2100, B=1, V=29, lmin=1000, lmax=1000),
+}
+
+
+@pytest.mark.parametrize("mode", ["throughput", "latency"])
+@pytest.mark.parametrize("name", sorted(SYNTH))
+def test_synthetic_vs_f64_oracle(name, mode):
+    from oracle import ctc_f64
+    acts, labels, al, ll = synth_problem(**SYNTH[name])
+    costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
+    oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
+    _assert_close(costs, grads, oc, og, name)
+    assert not (status & 0x8).any(), "range flag raised on a benign input"
+
+
+def test_edge_cases_batch():
+    """configs[4]: L=0, all-same labels at T=2L-2 / 2L-1 / 2L, T < L, T=1 with L in {0,1}, padded frames."""
+    from oracle import ctc_f64
+    rng = np.random.default_rng(99)
+    T, V = 24, 7
+    #        L=0   same x6 (need 11)          T<L   T=1,L=0  T=1,L=1  normal
+    ll = np.array([0, 6, 6, 6, 9, 0, 1, 5], np.int32)
+    al = np.array([24, 10, 11, 12, 8, 1, 1, 20], np.int32)
+    labels = np.concatenate([np.full(18, 3), rng.integers(1, V, 9), [4], rng.integers(1, V, 5)]).astype(np.int32)
+    acts = rng.standard_normal((T, len(ll), V)).astype(np.float32)
+    for mode in ("throughput", "latency"):
+        costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
+        oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
+        _assert_close(costs, grads, oc, og, "edge/" + mode)
+        assert costs[1] == 0.0 and not grads[:, 1].any() and status[1] & 0x1      # T = 2L-2: infeasible
+        assert costs[2] > 0 and costs[3] > 0 and costs[4] == 0.0 and status[4] & 0x1
+        for b in range(len(ll)):
+            assert not grads[al[b]:, b].any(), "padded frames must get zero gradient"
+        np.testing.assert_allclose(grads[:, [0, 2, 3, 5, 6, 7]].sum(-1)[:1], 0.0, atol=2e-6)
+
+
+def test_single_label_total():
+    """sum L = 1 (the reference's `.squeeze()` makes labels 0-dim in that case, data.py:157)."""
+    from aes_lac_2018_b200 import CTCLoss
+    from oracle import ctc_f64
+    rng = np.random.default_rng(3)
+    acts = rng.standard_normal((5, 1, 29)).astype(np.float32)
+    loss = CTCLoss()(torch.tensor(acts).cuda(), torch.tensor(7, dtype=torch.int32), torch.tensor([5], dtype=torch.int32),
+                     torch.tensor([1], dtype=torch.int32))
+    oc, _ = ctc_f64.ctc_batch(acts, [7], [5], [1])
+    assert loss.shape == (1,) and abs(loss.item() - oc[0]) <= LOSS_RTOL * oc[0]
+
+
+def test_strided_activations_no_copy():
+    """The reference hands over `out.transpose(0, 1)` of a B x T x V tensor (metrics.py:49, DataParallel
+    case of engine.py:15): strides (V, T*V, 1).  Must give the same numbers as the dense layout."""
+    acts, labels, al, ll = synth_problem(21, 120, 6, 29, 5, 40, tmin=90)
+    from aes_lac_2018_b200 import ctc_loss_raw
+    btv = torch.tensor(acts).cuda().transpose(0, 1).contiguous()          # B x T x V storage
+    view = btv.transpose(0, 1)                                            # T x B x V view, non-contiguous
+    assert not view.is_contiguous()
+    args = [torch.tensor(x) for x in (labels, al, ll)]
+    c1, g1, _ = ctc_loss_raw(view, *args)
+    c2, g2, _ = ctc_loss_raw(view.contiguous(), *args)
+    assert torch.equal(c1, c2) and torch.equal(g1, g2)
+
+
+def test_costs_only_matches_and_is_default_under_no_grad():
+    from aes_lac_2018_b200 import CTCLoss
+    acts, labels, al, ll = synth_problem(22, 150, 5, 29, 5, 50, tmin=100)
+    c_full, _, _ = _engine(acts, labels, al, ll)
+    c_only, g_none, _ = _engine(acts, labels, al, ll, want_grad=False)
+    assert g_none is None
+    np.testing.assert_array_equal(c_full, c_only)
+    a = torch.tensor(acts).cuda().requires_grad_()
+    with torch.no_grad():                                                 # eval metric path, engine.py:107
+        loss = CTCLoss()(a, torch.tensor(labels), torch.tensor(al), torch.tensor(ll))
+    assert not loss.requires_grad and abs(loss.item() - c_full.sum()) <= 1e-4 * c_full.sum()
+
+
+def test_module_drop_in_semantics():
+    """The operations the reference applies to the result (engine.py:22-30, 84, 94; metrics.py:51-55)."""
+    from aes_lac_2018_b200 import CTCLoss
+    from oracle import ctc_f64
+    import warpctc_pytorch
+    assert warpctc_pytorch.CTCLoss is CTCLoss
+    acts, labels, al, ll = synth_problem(23, 100, 4, 29, 5, 30, tmin=60)
+    B = acts.shape[1]
+    logits = torch.tensor(acts).cuda().requires_grad_()
+    out = logits * 1.0                                                     # non-leaf, like the model output
+    criterion = CTCLoss()
+    loss = criterion(out, torch.tensor(labels), torch.tensor(al), torch.tensor(ll))
+    assert loss.shape == (1,) and loss.device.type == "cpu" and loss.dtype == torch.float32
+    loss = loss / B
+    loss_sum = loss.sum()
+    assert len(loss_sum.shape) == 0 and not (loss_sum == float("inf"))
+    loss_sum.backward()
+    oc, og = ctc_f64.ctc_loss_module(acts, labels, al, ll)
+    assert abs(loss_sum.item() - oc / B) <= LOSS_RTOL * oc / B
+    assert np.abs(logits.grad.cpu().numpy() - og / B).max() <= GRAD_ATOL
+    # averaging flags of the upstream module
+    for kw, denom in ((dict(size_average=True), B), (dict(length_average=True), float(al.sum()))):
+        lg = torch.tensor(acts).cuda().requires_grad_()
+        l2 = CTCLoss(**kw)(lg, torch.tensor(labels), torch.tensor(al), torch.tensor(ll))
+        l2.sum().backward()
+        assert abs(l2.item() - oc / denom) <= LOSS_RTOL * oc / denom
+        assert np.abs(lg.grad.cpu().numpy() - og / denom).max() <= GRAD_ATOL
+    with pytest.raises(RuntimeError):
+        criterion(torch.tensor(acts), torch.tensor(labels), torch.tensor(al), torch.tensor(ll))   # CPU acts: no fallback
+
+
+def test_inf_cost_no_nan():
+    """upstream inf_test: a needed label has probability 0 everywhere => cost +inf, gradient finite."""
+    rng = np.random.default_rng(5)
+    T, V, L = 50, 15, 10
+    acts = rng.standard_normal((T, 1, V)).astype(np.float32)
+    labels = rng.integers(1, V, L).astype(np.int32)
+    labels[0] = 2
+    acts[:, 0, 2] = -1e30
+    costs, grads, status = _engine(acts, labels, [T], [L])
+    assert np.isinf(costs[0]) and costs[0] > 0 and np.isfinite(grads).all() and status[0] & 0x2
+
+
+def _opts(lib_mod, stream=0, blank=0, loc=1):
+    o = lib_mod.CtcOptions()
+    o.loc = loc
+    o.stream = stream
+    o.blank_label = blank
+    return o
+
+
+def test_warpctc_c_abi_entry_points():
+    """compute_ctc_loss / get_workspace_size with upstream's signature and pointer residency."""
+    from aes_lac_2018_b200 import _lib
+    from oracle import ctc_f64
+    lib = _lib.load()
+    assert lib.get_warpctc_version() == 2
+    acts, labels, al, ll = synth_problem(31, 90, 5, 29, 3, 30, tmin=50)
+    al[0] = 90
+    T, B, V = acts.shape
+    d_acts = torch.tensor(acts).cuda()
+    d_grads = torch.zeros_like(d_acts)                                     # upstream callers pre-zero
+    costs = np.zeros(B, np.float32)
+    need = ctypes.c_size_t(0)
+    st = lib.get_workspace_size(ll.ctypes.data, al.ctypes.data, V, B, _opts(_lib), ctypes.byref(need))
+    assert st == 0 and need.value > 0
+    ws = torch.empty(need.value, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    st = lib.compute_ctc_loss(d_acts.data_ptr(), d_grads.data_ptr(), labels.ctypes.data, ll.ctypes.data, al.ctypes.data,
+                              V, B, costs.ctypes.data, ws.data_ptr(), _opts(_lib))
+    assert st == 0, _lib.status_string(lib, st)
+    oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
+    _assert_close(costs.astype(np.float64), d_grads.cpu().numpy().astype(np.float64), oc, og, "c-abi")
+    # costs only (gradients == NULL)
+    costs2 = np.zeros(B, np.float32)
+    st = lib.compute_ctc_loss(d_acts.data_ptr(), None, labels.ctypes.data, ll.ctypes.data, al.ctypes.data,
+                              V, B, costs2.ctypes.data, ws.data_ptr(), _opts(_lib))
+    assert st == 0 and np.array_equal(costs, costs2)
+    # error behaviour: status codes, never exceptions
+    assert lib.compute_ctc_loss(None, None, labels.ctypes.data, ll.ctypes.data, al.ctypes.data, V, B,
+                                costs.ctypes.data, ws.data_ptr(), _opts(_lib)) == 2
+    assert lib.compute_ctc_loss(d_acts.data_ptr(), None, labels.ctypes.data, ll.ctypes.data, al.ctypes.data, V, B,
+                                costs.ctypes.data, ws.data_ptr(), _opts(_lib, loc=0)) == 2       # CTC_CPU: no CPU path
+    bad = labels.copy()
+    bad[0] = V + 3
+    assert lib.compute_ctc_loss(d_acts.data_ptr(), None, bad.ctypes.data, ll.ctypes.data, al.ctypes.data, V, B,
+                                costs.ctypes.data, ws.data_ptr(), _opts(_lib)) == 2
+    too_long = np.array([5000], np.int32)
+    assert lib.get_workspace_size(too_long.ctypes.data, np.array([20000], np.int32).ctypes.data, V, 1, _opts(_lib),
+                                  ctypes.byref(need)) == 4
+
+
+def test_full_size_properties_c4():
+    """BASELINE configs[3] shape (T=1500, V=29, L<=200) at a batch the oracle cannot cover: check
+    size-independent properties and spot-check a few utterances against the oracle."""
+    from aes_lac_2018_b200 import ctc_loss_raw
+    from oracle import ctc_f64
+    B, T, V = 512, 1500, 29
+    g = torch.Generator().manual_seed(1234)
+    acts = torch.randn(T, B, V, generator=g)
+    ll = torch.randint(50, 201, (B,), generator=g, dtype=torch.int32)
+    al = torch.full((B,), T, dtype=torch.int32)
+    labels = torch.randint(1, V, (int(ll.sum()),), generator=g, dtype=torch.int32)
+    costs, grads, status = ctc_loss_raw(acts.cuda(), labels, al, ll)
+    assert not status.any()
+    assert torch.isfinite(costs).all() and torch.isfinite(grads).all()
+    assert grads.sum(-1).abs().max().item() < 5e-6                        # rows sum to zero
+    # batch independence: utterance b alone gives bit-identical numbers
+    offs = torch.cumsum(ll, 0) - ll
+    for b in (0, 77, 511):
+        lab_b = labels[offs[b]:offs[b] + ll[b]]
+        c1, g1, _ = ctc_loss_raw(acts[:, b:b + 1].cuda(), lab_b, al[b:b + 1], ll[b:b + 1], mode="throughput")
+        assert torch.equal(c1[0], costs[b]) and torch.equal(g1[:, 0], grads[:, b])
+        oc, og = ctc_f64.ctc_batch(acts[:, b:b + 1].numpy(), lab_b.numpy(), [T], [int(ll[b])])
+        _assert_close(c1.numpy().astype(np.float64), g1.cpu().numpy().astype(np.float64), oc, og, f"c4 utt {b}")

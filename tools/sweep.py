@@ -1,0 +1,73 @@
+"""Developer timing sweep (not the contract bench): device time of one engine call per configuration.
+Usage (on the GPU box): python tools/sweep.py [--quick]"""
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from aes_lac_2018_b200 import ctc_loss_raw
+
+
+def problem(B, T, V, lmin, lmax, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    acts = torch.randn(T, B, V, generator=g)
+    ll = torch.randint(lmin, lmax + 1, (B,), generator=g, dtype=torch.int32)
+    al = torch.full((B,), T, dtype=torch.int32)
+    labels = torch.randint(1, V, (int(ll.sum()),), generator=g, dtype=torch.int32)
+    return acts.cuda(), labels, al, ll
+
+
+def time_call(fn, iters=5, warm=2, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    quick = "--quick" in sys.argv
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rows = []
+    cfgs = [
+        ("c1", 4, 200, 29, 10, 50), ("c2", 32, 750, 29, 50, 200), ("b256", 256, 750, 29, 50, 200),
+        ("b1024", 1024, 750, 29, 50, 200), ("b4096", 4096, 750, 29, 50, 200),
+        ("c4", 1024, 1500, 29, 50, 200), ("L200", 2048, 750, 29, 200, 200), ("L60", 2048, 750, 29, 60, 60),
+    ]
+    if quick:
+        cfgs = cfgs[:4]
+    for name, B, T, V, lmin, lmax in cfgs:
+        acts, labels, al, ll = problem(B, T, V, lmin, lmax)
+        for mode in ("throughput", "latency"):
+            if mode == "latency" and B > 1024:
+                continue
+            for want_grad in (True, False):
+                try:
+                    med, best = time_call(lambda: ctc_loss_raw(acts, labels, al, ll, want_grad=want_grad, mode=mode), flush=flush)
+                except Exception as e:  # noqa: BLE001
+                    print(name, mode, want_grad, "FAILED", e)
+                    continue
+                alg = (8 if want_grad else 4) * T * V * B + 4 * int(ll.sum()) + 12 * B
+                row = dict(cfg=name, B=B, T=T, V=V, mode=mode, grad=want_grad, ms_med=round(med, 4), ms_best=round(best, 4),
+                           utt_per_s=round(B / med * 1e3), alg_GBs=round(alg / med / 1e6, 1))
+                rows.append(row)
+                print(json.dumps(row), flush=True)
+        del acts
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(rows, open("gpurun_out/sweep.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
