@@ -49,6 +49,7 @@ class CtcB200Call(ctypes.Structure):
         ("workspace_bytes", ctypes.c_size_t),
         ("stream", ctypes.c_void_p),
         ("flags", ctypes.c_uint),
+        ("debug_device", ctypes.c_void_p),
     ]
 
 

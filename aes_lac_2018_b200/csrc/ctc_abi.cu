@@ -196,6 +196,7 @@ ctcStatus_t run(const ctcB200Call &c)
     P.costs = d_costs; P.status = d_status;
     P.V = V; P.T_max = c.max_time; P.B = B; P.blank = c.blank_label;
     P.grad_scale = c.grad_scale;
+    P.debug = c.debug_device;
 
     for (const Plan::Launch &l : plan.launches) {
         P.utt_ids = d_meta + 3 * B + l.first;

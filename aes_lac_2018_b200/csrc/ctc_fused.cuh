@@ -57,6 +57,7 @@ struct FusedParams {
     long long ckpt_stride;            // doubles per CTA slot
     int V, T_max, B, blank;
     float grad_scale;
+    long long *debug;                 // optional [B][4]: fwd cycles, total cycles, total ns, smid
 };
 
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
@@ -109,6 +110,18 @@ template <int W>
 __device__ __forceinline__ void cta_sync()
 {
     if (W == 1) __syncwarp(); else __syncthreads();
+}
+// p~ = exp(x) for x <= 0 as a double with fp32 mantissa accuracy but fp64 exponent range: 2^frac by
+// MUFU.EX2, integer part added to the double's exponent field.  Keeps relative accuracy ~2^-22 down to
+// exp(-708) (a float would go denormal below exp(-87) and lose bits; warp-ctc clamps/underflows there).
+__device__ __forceinline__ double exp_wide(float x)
+{
+    const float y = x * 1.4426950408889634f;               // log2(e)
+    const float yi = floorf(y);
+    if (!(yi > -1000.f)) return 0.0;                        // also catches NaN/-inf
+    const float m = exp2f(y - yi);                          // [1, 2]
+    const double d = (double)m;
+    return __hiloint2double(__double2hiint(d) + (int)yi * (1 << 20), __double2loint(d));
 }
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 {
@@ -194,6 +207,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     unsigned *scratch = (unsigned *)(smem + lay.off_scr);   // [W] cross-warp max
 
     const int b = P.utt_ids[blockIdx.x];
+    long long dbg_c0 = 0, dbg_n0 = 0, dbg_c1 = 0;
+    if (P.debug && tid == 0) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_n0));
+    }
     const int T = P.act_len[b];
     const int L = P.label_len[b];
     const int S = 2 * L + 1;
@@ -301,9 +319,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             float s = 0.f;
             double *prow = ptab + r * PST;
             if (act) for (int k = g; k < V; k += G) {
-                const float e = __expf(row[k] - m);
-                s += e;
-                prow[k] = (double)e;
+                const double e = exp_wide(row[k] - m);
+                s += (float)e;
+                prow[k] = e;
             }
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -400,8 +418,22 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         else cost = INFINITY;
         P.costs[b] = cost;
     }
+    if (P.debug && tid == 0) dbg_c1 = clock64();
+    auto dbg_out = [&]() {
+        if (P.debug && tid == 0) {
+            long long n1;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.debug[b * 4 + 0] = dbg_c1 - dbg_c0;
+            P.debug[b * 4 + 1] = clock64() - dbg_c0;
+            P.debug[b * 4 + 2] = n1 - dbg_n0;
+            P.debug[b * 4 + 3] = smid;
+        }
+    };
     if (!want_grad) {
         if (tid == 0) P.status[b] = ustat;
+        dbg_out();
         return;
     }
 
@@ -538,6 +570,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     // padded frames get zero gradient
     for (int t = T + warp; t < P.T_max; t += W)
         for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
+    dbg_out();
 }
 
 }  // namespace ctcb200

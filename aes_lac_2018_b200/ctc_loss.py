@@ -35,7 +35,7 @@ def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
-                 grad_scale: float = 1.0, mode: str = "auto"):
+                 grad_scale: float = 1.0, mode: str = "auto", debug: torch.Tensor | None = None):
     """Runs the CUDA engine once.  Returns (costs[B] float32 CPU tensor, grads[T,B,V] CUDA tensor or None,
     status[B] int32 CPU tensor).  `acts` may be any T x B x V view whose last stride is 1."""
     lib = _lib.load()
@@ -87,6 +87,7 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         call.workspace = workspace.data_ptr()
         call.workspace_bytes = need.value
         call.stream = torch.cuda.current_stream(acts_d.device).cuda_stream
+        call.debug_device = debug.data_ptr() if debug is not None else None
         call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY}[mode]
         st = lib.ctc_b200_compute(ctypes.byref(call))
         if st != _lib.CTC_STATUS_SUCCESS:

@@ -21,7 +21,7 @@
  *     does this on its CPU path only; its GPU path leaves the cost slot unwritten).
  *   - Labels ARE validated: a label outside [0, alphabet_size) or equal to the blank returns
  *     CTC_STATUS_INVALID_VALUE (upstream reads out of bounds).
- *   - The blank-extended sequence may be up to 8193 states long (L <= 4096); upstream's GPU path stops
+ *   - The blank-extended sequence may be up to 4095 states long (L <= 2047); upstream's GPU path stops
  *     at 1280 states (L <= 639) with CTC_STATUS_UNKNOWN_ERROR.  Beyond the limit this library also
  *     returns CTC_STATUS_UNKNOWN_ERROR.
  */
@@ -136,6 +136,8 @@ typedef struct ctcB200Call {
     size_t workspace_bytes;
     CUstream stream;
     unsigned int flags;
+    long long *debug_device;    /* DEVICE [minibatch][4] or NULL: per-utterance {forward cycles, total cycles,
+                                   total ns, SM id} -- profiling aid, not part of the result */
 } ctcB200Call;
 
 /* per-utterance status bits (status_host) */
