@@ -13,6 +13,7 @@ CTC_GPU = 1
 FLAG_NO_SYNC = 0x1
 FLAG_MODE_THROUGHPUT = 1 << 8
 FLAG_MODE_LATENCY = 2 << 8
+FLAG_MODE_THROUGHPUT_K8 = 3 << 8
 
 UTT_INFEASIBLE, UTT_INF_COST, UTT_BAD_LABEL, UTT_RANGE = 1, 2, 4, 8
 

@@ -46,6 +46,13 @@ const Variant kThroughput[] = {
     CTC_VARIANT(10, 1, 16), CTC_VARIANT(12, 1, 16), CTC_VARIANT(14, 1, 16), CTC_VARIANT(16, 1, 16),
     CTC_VARIANT(16, 2, 16), CTC_VARIANT(16, 4, 8),  CTC_VARIANT(16, 8, 4),
 };
+// Same ladder with 8-step chunks: half the shared memory per CTA (more CTAs per SM), twice the
+// checkpoint traffic and per-chunk overhead.
+const Variant kThroughput8[] = {
+    CTC_VARIANT(2, 1, 8),  CTC_VARIANT(4, 1, 8),  CTC_VARIANT(6, 1, 8),  CTC_VARIANT(8, 1, 8),
+    CTC_VARIANT(10, 1, 8), CTC_VARIANT(12, 1, 8), CTC_VARIANT(14, 1, 8), CTC_VARIANT(16, 1, 8),
+    CTC_VARIANT(16, 2, 8), CTC_VARIANT(16, 4, 8), CTC_VARIANT(16, 8, 4),
+};
 // Latency ladder (few utterances in flight): more warps per utterance, fewer states per thread.
 const Variant kLatency[] = {
     CTC_VARIANT(2, 1, 16), CTC_VARIANT(2, 2, 16), CTC_VARIANT(2, 4, 16), CTC_VARIANT(4, 4, 16),
@@ -53,6 +60,7 @@ const Variant kLatency[] = {
 };
 constexpr int kNumThroughput = sizeof(kThroughput) / sizeof(Variant);
 constexpr int kNumLatency = sizeof(kLatency) / sizeof(Variant);
+constexpr int kNumThroughput8 = sizeof(kThroughput8) / sizeof(Variant);
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
 
@@ -103,8 +111,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     // mode: 0 auto, 1 throughput ladder, 2 latency ladder.  Auto: with fewer utterances than ~2 per SM
     // the T-serial chain is the bound, so spend more warps per utterance.
     plan.latency = (mode == 2) || (mode == 0 && B <= 296);
-    const Variant *ladder = plan.latency ? kLatency : kThroughput;
-    const int nl = plan.latency ? kNumLatency : kNumThroughput;
+    const Variant *ladder = plan.latency ? kLatency : (mode == 3 ? kThroughput8 : kThroughput);
+    const int nl = plan.latency ? kNumLatency : (mode == 3 ? kNumThroughput8 : kNumThroughput);
 
     // bucket utterances by variant, longest first inside a bucket (tail balance)
     std::vector<std::pair<int, int>> order(B);       // (variant index, b)
@@ -259,15 +267,16 @@ ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_l
                                     int minibatch, int max_time, int want_gradients, size_t *size_bytes)
 {
     if (!size_bytes) return fail(CTC_STATUS_INVALID_VALUE, "null size_bytes");
-    Plan a, b;
-    // the ladder choice is deterministic in (B), so one plan suffices; take the max of both modes so a
-    // forced mode never overruns the workspace
-    ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
-                               want_gradients != 0, 1, a);
-    if (st != CTC_STATUS_SUCCESS) return st;
-    st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time, want_gradients != 0, 2, b);
-    if (st != CTC_STATUS_SUCCESS) return st;
-    *size_bytes = std::max(a.total, b.total);
+    // take the max over the ladders so that a forced mode never overruns the workspace
+    size_t need = 0;
+    for (int mode = 1; mode <= 3; ++mode) {
+        Plan p;
+        ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
+                                   want_gradients != 0, mode, p);
+        if (st != CTC_STATUS_SUCCESS) return st;
+        need = std::max(need, p.total);
+    }
+    *size_bytes = need;
     return CTC_STATUS_SUCCESS;
 }
 

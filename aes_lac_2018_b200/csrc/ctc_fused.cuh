@@ -7,23 +7,25 @@
 // Maths: SURVEY.md Appendix C.  This is not warp-ctc's algorithm organisation:
 //
 //  * LINEAR-domain fp64 recursion with exact power-of-two rescaling every K timesteps.  B200's fp64
-//    pipe issues 64 DFMA/clk/SM; a log-space cell costs 3-4 MUFU (16/clk/SM).  A linear cell is
-//    2 (blank) or 3 (label) fp64 ops and is accurate to ~1e-16/step, so the gradient lands within
-//    ~5e-7 of the float64 oracle at every BASELINE shape (warp-ctc's own fp32 log-space arithmetic is
-//    1e-3..1e-2 away; tests/proto_scaled_linear.py models the scheme on the CPU).
+//    pipe issues 64 DFMA/clk/SM (measured 58, tools/ubench.cu); a log-space cell costs 3-4 MUFU
+//    (16/clk/SM).  A linear cell is 2 (blank) or 3 (label) fp64 ops and is accurate to ~1e-16 per step,
+//    so the gradient lands within ~5e-7 of the float64 oracle at every BASELINE shape (warp-ctc's own fp32
+//    log-space arithmetic is 1e-3..1e-2 away; tests/proto_scaled_linear.py models the scheme on the CPU).
 //  * The softmax is fused in: each CTA stages K rows of raw activations with cp.async (prefetched one
-//    chunk ahead of the T-serial chain), exponentiates them once per sweep (fp32 ex2) into a shared
-//    table of UNNORMALISED p~ = exp(a - rowmax) stored as doubles.  Row sums only enter the loss
-//    (sum_t log rowsum_t, fp64) and the final p = p~/rowsum of the gradient: they cancel in the posterior.
+//    chunk ahead of the T-serial chain), exponentiates them once per sweep (MUFU.EX2 on the fraction,
+//    integer part added to the fp64 exponent => full relative accuracy down to exp(-700)) into a shared,
+//    symbol-major table of UNNORMALISED p~ = exp(a - rowmax).  Row sums only enter the loss
+//    (sum_t log rowsum_t) and the final p = p~/rowsum of the gradient: they cancel in the posterior.
 //  * No alpha spill to HBM.  The forward sweep checkpoints the (rescaled) alpha column once per chunk
 //    (8*S bytes per K steps); the backward sweep re-runs alpha inside the chunk from the checkpoint
-//    into shared memory, then runs beta over the same chunk and forms alpha*beta there.
+//    into shared memory, then runs beta over the same chunk, overwriting each alpha with alpha*beta.
 //  * Each thread owns NS consecutive states of the blank-extended sequence in registers; neighbours
 //    come by warp shuffle (one fp64 value per step for alpha, two for beta), across warps through a
 //    double-buffered shared slot and one barrier per step.  W = 1 needs no block barrier at all.
-//  * Per-symbol accumulation of alpha*beta is a deterministic gather: label products go to shared
-//    memory, thread k sums the positions of symbol k (list built once per utterance, ascending),
-//    blanks are reduced by shuffle.  Gradient rows are written coalesced, padded frames zeroed.
+//    The K steps of a chunk are fully unrolled so every shared-memory operand is [register + immediate].
+//  * Per-symbol accumulation of alpha*beta is a deterministic gather done once per chunk: thread k sums,
+//    for all K timesteps at once, the positions of symbol k (list built once per utterance, ascending);
+//    blank products are pre-summed per thread.  Gradient rows are written coalesced, padded frames zeroed.
 //
 // Thread/state map: thread tid owns states s = tid*NS + i, i < NS (NS even => even i are blanks).
 #pragma once
@@ -62,26 +64,24 @@ struct FusedParams {
 
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
 struct SmemLayout {
-    int pst;        // ptab row stride in doubles (odd, >= V+1)
-    int off_ptab, off_acol, off_gam, off_xch, off_zfin, off_raw, off_rinv, off_bpart, off_ea,
+    int off_ptab, off_acol, off_bpart, off_btot, off_xch, off_zfin, off_raw, off_rinv, off_ea,
         off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, total;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int NS, int W, int kChunk, int V, int T_max)
+__host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, int T_max)
 {
     SmemLayout l;
     const int NT = 32 * W, SP = NS * NT, LP = SP / 2;
-    const int nC = (T_max + kChunk - 1) / kChunk;
-    l.pst = (V + 1) | 1;
+    const int nC = (T_max + K - 1) / K;
     int o = 0;
-    l.off_ptab = o;  o += kChunk * l.pst * 8;
-    l.off_acol = o;  o += kChunk * SP * 8;
-    l.off_gam = o;   o += 2 * LP * 8;
+    l.off_ptab = o;  o += (V + 1) * (K + 1) * 8;          // [V+1][K+1] doubles, row V = zeros
+    l.off_acol = o;  o += K * SP * 8;                       // [K][NS][NT] doubles
+    l.off_bpart = o; o += K * NT * 8;                       // [K][NT] doubles: per-thread blank products
+    l.off_btot = o;  o += K * 8;                            // [K] doubles
     l.off_xch = o;   o += 2 * W * 2 * 8;
-    l.off_zfin = o;  o += 2 * 8;
-    l.off_raw = o;   o += 2 * kChunk * V * 4;
-    l.off_rinv = o;  o += kChunk * 4;
-    l.off_bpart = o; o += 2 * W * 4;
+    l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
+    l.off_raw = o;   o += 2 * K * V * 4;
+    l.off_rinv = o;  o += K * 4;
     l.off_ea = o;    o += (nC + 1) * 4;
     l.off_lab = o;   o += LP * 4;
     l.off_pos = o;   o += LP * 4;
@@ -98,30 +98,39 @@ __device__ __forceinline__ double pow2d(int e)            // 2^e, e in [-1022, 1
 {
     return __hiloint2double((e + 1023) << 20, 0);
 }
-__device__ __forceinline__ double shfl_up_d(double v)
-{
-    return __shfl_up_sync(0xffffffffu, v, 1);
-}
-__device__ __forceinline__ double shfl_down_d(double v)
-{
-    return __shfl_down_sync(0xffffffffu, v, 1);
-}
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_down_d(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
 template <int W>
 __device__ __forceinline__ void cta_sync()
 {
     if (W == 1) __syncwarp(); else __syncthreads();
 }
-// p~ = exp(x) for x <= 0 as a double with fp32 mantissa accuracy but fp64 exponent range: 2^frac by
-// MUFU.EX2, integer part added to the double's exponent field.  Keeps relative accuracy ~2^-22 down to
-// exp(-708) (a float would go denormal below exp(-87) and lose bits; warp-ctc clamps/underflows there).
-__device__ __forceinline__ double exp_wide(float x)
+__device__ __forceinline__ float ex2_approx(float x)
 {
-    const float y = x * 1.4426950408889634f;               // log2(e)
-    const float yi = floorf(y);
-    if (!(yi > -1000.f)) return 0.0;                        // also catches NaN/-inf
-    const float m = exp2f(y - yi);                          // [1, 2]
-    const double d = (double)m;
-    return __hiloint2double(__double2hiint(d) + (int)yi * (1 << 20), __double2loint(d));
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// p~ = exp(d), d = a - rowmax <= 0, as a double with fp32-mantissa accuracy and fp64 exponent range.
+// d*log2(e) is split into integer + fraction (magic-number rounding, no F2I/FRND); the product's rounding
+// error is compensated with two FFMAs so the relative accuracy stays ~2^-22 for |d| up to ~700
+// (a plain float exp goes denormal below exp(-87); warp-ctc clamps / underflows there).
+__device__ __forceinline__ double exp_wide(float d)
+{
+    const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.925963033500011e-8f;
+    const bool is_nan = !(d == d);                          // NaN activations must poison the cost, not vanish
+    d = fmaxf(d, -800.f);
+    const float yh = d * L2E_HI;
+    const float yl = fmaf(d, L2E_LO, fmaf(d, L2E_HI, -yh));
+    const float MAGIC = 12582912.f;                         // 1.5 * 2^23
+    const float t = yh + MAGIC;
+    const float yi = t - MAGIC;                             // nearest integer to yh
+    const float fr = (yh - yi) + yl;                        // [-0.5, 0.5]
+    const double m = (double)ex2_approx(fr);                // [0.707, 1.415]
+    const int e = __float_as_int(t) - 0x4B400000;           // integer part (<= 0)
+    const double r = __hiloint2double(__double2hiint(m) + e * (1 << 20), __double2loint(m));
+    return is_nan ? (double)NAN : ((e < -1000) ? 0.0 : r);
 }
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 {
@@ -169,7 +178,8 @@ __device__ __forceinline__ void rescale(double (&x)[NS], int &E, unsigned *scrat
 }
 
 // ---- the kernel ----------------------------------------------------------------------------------
-// K = timesteps per chunk (rescale / checkpoint / softmax granularity)
+// NS states per thread, W warps per utterance, K timesteps per chunk (rescale / checkpoint / softmax /
+// gather granularity).
 template <int NS, int W, int K>
 __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 {
@@ -178,28 +188,30 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int SP = NS * NT;                // padded state count
     constexpr int LP = SP / 2;                 // padded label count
     constexpr int NL = NS / 2;                 // labels per thread
-    constexpr int kChunk = K;
+    constexpr int KP = K + 1;                  // ptab row stride (doubles)
     constexpr int G = (NT / K) < 32 ? (NT / K) : 32;   // lanes per softmax row
     constexpr int RP = NT / G;                 // rows per softmax pass
     constexpr int NPASS = (K + RP - 1) / RP;
-    static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0, "bad softmax group");
+    constexpr int TG = (K >= W) ? K / W : 1;   // timesteps per gather item
+    constexpr int NG = K / TG;                 // gather items per symbol
+    constexpr int RB = (NT / K) < 32 ? (NT / K) : 32;  // lanes per timestep in the blank reduction
+    static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
 
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = P.V, blank = P.blank;
     const SmemLayout lay = make_layout(NS, W, K, V, P.T_max);
-    const int PST = lay.pst;
-    double *ptab = (double *)(smem + lay.off_ptab);         // [K][PST]  p~ as doubles, slot V = 0.0
-    double *acol = (double *)(smem + lay.off_acol);         // [K][NS][NT] recomputed alpha columns
-    double *gam = (double *)(smem + lay.off_gam);           // [2][LP]   alpha*beta of label states
+    double *ptab = (double *)(smem + lay.off_ptab);         // [V+1][KP]  p~ as doubles (symbol-major)
+    double *acol = (double *)(smem + lay.off_acol);         // [K][NS][NT] alpha columns, then alpha*beta
+    double *bpart = (double *)(smem + lay.off_bpart);       // [K][NT]   per-thread sum of blank alpha*beta
+    double *btot = (double *)(smem + lay.off_btot);         // [K]
     double *xch = (double *)(smem + lay.off_xch);           // [2][W][2] cross-warp boundary values
-    double *zfin = (double *)(smem + lay.off_zfin);         // [2]
+    double *zfin = (double *)(smem + lay.off_zfin);         // [2] + [32] per-warp logsum
     float *raw = (float *)(smem + lay.off_raw);             // [2][K][V] staged raw activations
     float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum
-    float *bpart = (float *)(smem + lay.off_bpart);         // [2][W] blank posterior partials
     int *ea_s = (int *)(smem + lay.off_ea);                 // [nC] alpha exponent per chunk
     int *lab_s = (int *)(smem + lay.off_lab);               // [LP]
-    int *pos_s = (int *)(smem + lay.off_pos);               // [LP] label indices grouped by symbol
+    int *pos_s = (int *)(smem + lay.off_pos);               // [LP] acol element offsets grouped by symbol
     int *cnt_s = (int *)(smem + lay.off_cnt);               // [V+1]
     int *off_s = (int *)(smem + lay.off_off);               // [V+1]
     int *misc = (int *)(smem + lay.off_misc);               // [0] repeats, [1] bad label
@@ -252,18 +264,19 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 
     // ---- per-thread label constants ----
     const int j0 = tid * NL;
-    int poff[NL];                                           // byte offset of p~(label) inside a ptab row
-    unsigned mbits = 0;                                     // bit jj: skip INTO label j0+jj allowed
+    int poff[NL];                                           // byte offset of symbol row inside ptab
+    double msk[NL + 1];                                     // 1.0 if the skip INTO label j0+jj is allowed
 #pragma unroll
     for (int jj = 0; jj <= NL; ++jj) {
         const int j = j0 + jj;
         const int cur = (j < LP) ? lab_s[j] : -1;
         const int prv = (j >= 1 && j - 1 < LP) ? lab_s[j - 1] : -1;
-        if (jj < NL) poff[jj] = (cur < 0 ? V : cur) * 8;
-        if (cur >= 0 && j >= 1 && cur != prv) mbits |= (1u << jj);
+        if (jj < NL) poff[jj] = lay.off_ptab + (cur < 0 ? V : cur) * (KP * 8);
+        msk[jj] = (cur >= 0 && j >= 1 && cur != prv) ? 1.0 : 0.0;
     }
+    const int pboff = lay.off_ptab + blank * (KP * 8);
 
-    // ---- per-symbol position lists (deterministic, ascending) ----
+    // ---- per-symbol position lists (deterministic, ascending); entries are acol element offsets ----
     if (want_grad) {
         for (int k = tid; k <= V; k += NT) {
             int c = 0;
@@ -279,20 +292,26 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         __syncthreads();
         for (int k = tid; k < V; k += NT) {
             int q = off_s[k];
-            if (cnt_s[k]) for (int j = 0; j < L; ++j) if (lab_s[j] == k) pos_s[q++] = j;
+            if (cnt_s[k])
+                for (int j = 0; j < L; ++j)
+                    if (lab_s[j] == k) {
+                        const int s = 2 * j + 1;
+                        pos_s[q++] = (s % NS) * NT + (s / NS);      // [i][tid] offset inside one acol column
+                    }
         }
     }
     if (tid < 2 * W * 2) xch[tid] = 0.0;
     if (tid < 2) zfin[tid] = 0.0;
+    for (int i = tid; i < KP; i += NT) ptab[V * KP + i] = 0.0;       // the "no label here" row
     __syncthreads();
 
-    const int nC = (T + kChunk - 1) / kChunk;
+    const int nC = (T + K - 1) / K;
     double *ck = P.ckpt + (long long)blockIdx.x * P.ckpt_stride;
 
     // raw-activation prefetch of chunk c into buffer c&1 (rows spread over warps, k over lanes)
     auto prefetch = [&](int c) {
-        const int t0 = c * kChunk, n = min(kChunk, T - t0);
-        float *dst = raw + (c & 1) * kChunk * V;
+        const int t0 = c * K, n = min(K, T - t0);
+        float *dst = raw + (c & 1) * K * V;
         for (int r = warp; r < n; r += W) {
             const float *src = acts_b + (long long)(t0 + r) * P.act_stride_t;
             for (int k = lane; k < V; k += 32) cp_async4(dst + r * V + k, src + k);
@@ -301,11 +320,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     };
 
     // softmax of the staged chunk -> ptab (unnormalised p~, fp64), rinv; returns sum_r log(rowsum_r)
-    auto softmax_chunk = [&](int c, bool want_log) -> double {
-        const int n = min(kChunk, T - c * kChunk);
-        const float *src = raw + (c & 1) * kChunk * V;
+    auto softmax_chunk = [&](int c, bool want_log) -> float {
+        const int n = min(K, T - c * K);
+        const float *src = raw + (c & 1) * K * V;
         const int g = tid % G;
-        double lg = 0.0;
+        float lg = 0.f;
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
             const int r = tid / G + ps * RP;
@@ -316,26 +335,26 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (m == -INFINITY) m = 0.f;
-            float s = 0.f;
-            double *prow = ptab + r * PST;
+            double s = 0.0;
             if (act) for (int k = g; k < V; k += G) {
                 const double e = exp_wide(row[k] - m);
-                s += (float)e;
-                prow[k] = e;
+                s += e;
+                ptab[k * KP + r] = e;
             }
 #pragma unroll
-            for (int o = G / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            for (int o = G / 2; o >= 1; o >>= 1) s += shfl_xor_d(s, o);
             if (act && g == 0) {
-                prow[V] = 0.0;                              // the "no label here" slot
-                rinv[r] = (s > 0.f) ? 1.f / s : 0.f;
-                if (want_log) lg += log((double)s);
+                const float sf = (float)s;                  // in [1, V]
+                rinv[r] = (sf > 0.f) ? 1.f / sf : 0.f;
+                if (want_log) lg += __logf(sf);
             }
         }
         return lg;
     };
 
-    // one alpha step in place (descending i keeps old neighbours intact)
-    auto alpha_step = [&](double (&a)[NS], const double *prow, int &par) {
+    // one alpha step in place (descending i keeps old neighbours intact); tt is a compile-time constant
+    // after unrolling, so every shared operand is [register + immediate]
+    auto alpha_step = [&](double (&a)[NS], int tt, int &par) {
         double up1 = shfl_up_d(a[NS - 1]);
         if (W > 1) {
             if (lane == 31) xch[(par * W + warp) * 2] = a[NS - 1];
@@ -343,19 +362,16 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             if (lane == 0) up1 = (warp > 0) ? xch[(par * W + warp - 1) * 2] : 0.0;
             par ^= 1;
         } else if (lane == 0) up1 = 0.0;
-        const double pb = prow[blank];
+        const double pb = *(const double *)(smem + pboff + tt * 8);
 #pragma unroll
         for (int i = NS - 1; i >= 0; --i) {
             if (i & 1) {
                 const int jj = i >> 1;
-                const double pl = *(const double *)((const char *)prow + poff[jj]);
-                double s = a[i] + a[i - 1];
+                const double pl = *(const double *)(smem + poff[jj] + tt * 8);
                 const double p2 = (i >= 2) ? a[i - 2] : up1;
-                if ((mbits >> jj) & 1u) s += p2;
-                a[i] = s * pl;
+                a[i] = fma(msk[jj], p2, a[i] + a[i - 1]) * pl;
             } else {
-                const double s = a[i] + ((i >= 1) ? a[i - 1] : up1);
-                a[i] = s * pb;
+                a[i] = (a[i] + ((i >= 1) ? a[i - 1] : up1)) * pb;
             }
         }
     };
@@ -367,6 +383,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     if (tid == 0) a[0] = pow2d(kTargetExp);                 // virtual column t = -1
     int Ea = -kTargetExp;
     int par = 0;
+    float logsum_f = 0.f;
     double logsum = 0.0;
 
     prefetch(0);
@@ -380,12 +397,17 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         cp_async_wait_all();
         cta_sync<W>();                                      // raw chunk visible; previous ptab readers done
         if (c + 1 < nC) prefetch(c + 1);
-        logsum += softmax_chunk(c, true);
+        logsum_f += softmax_chunk(c, true);
+        if ((c & 15) == 15) { logsum += (double)logsum_f; logsum_f = 0.f; }
         cta_sync<W>();
-        const int n = min(kChunk, T - c * kChunk);
-#pragma unroll 1
-        for (int tt = 0; tt < n; ++tt) alpha_step(a, ptab + tt * PST, par);
+        const int n = min(K, T - c * K);
+#pragma unroll
+        for (int tt = 0; tt < K; ++tt) {
+            if (tt >= n) break;
+            alpha_step(a, tt, par);
+        }
     }
+    logsum += (double)logsum_f;
 
     // Z^ = alpha^_{T-1}(S-1) + alpha^_{T-1}(S-2)
 #pragma unroll
@@ -394,21 +416,19 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         if (s == S - 1) zfin[0] = a[i];
         if (s == S - 2) zfin[1] = a[i];
     }
-    // sum_t log(rowsum_t): reduce the per-thread partials (fp64) through shared memory
+    // sum_t log(rowsum_t): reduce the per-thread partials through shared memory
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) logsum += __shfl_xor_sync(0xffffffffu, logsum, o);
-    __syncthreads();
-    if (lane == 0) gam[warp] = logsum;
+    for (int o = 16; o >= 1; o >>= 1) logsum += shfl_xor_d(logsum, o);
+    if (lane == 0) zfin[2 + warp] = logsum;
     __syncthreads();
     const double zhat = zfin[0] + zfin[1];
     const int Ea_fin = Ea;
     {
         double ls = 0.0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) ls += gam[w];
+        for (int w = 0; w < W; ++w) ls += zfin[2 + w];
         logsum = ls;
     }
-    __syncthreads();                                        // gam reused below
     const bool z_ok = (zhat > 0.0) && (zhat < INFINITY);
     if (!(zhat == zhat) || zhat == INFINITY) ustat |= UTT_RANGE;
     else if (!z_ok) ustat |= UTT_INF_COST;
@@ -443,11 +463,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
     for (int i = 0; i < NS; ++i) bt[i] = (tid * NS + i == S - 1) ? pow2d(kTargetExp) : 0.0;   // virtual column t = T
     int Eb = -kTargetExp;
-    int gpar = 0;                                           // parity of gam / bpart / beta-xch buffers
+    int bpar = 0;                                           // parity of the beta boundary buffers
     float chk_dev = 0.f;                                    // max |sum_k posterior - 1| seen by this thread
 
     for (int c = nC - 1; c >= 0; --c) {
-        const int t0 = c * kChunk, n = min(kChunk, T - t0);
+        const int t0 = c * K, n = min(K, T - t0);
         if (c < nC - 1) {                                   // ptab still holds the last chunk after the forward sweep
             cp_async_wait_all();
             cta_sync<W>();
@@ -461,99 +481,112 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
         for (int i = 0; i < NS; ++i) a[i] = ck[((long long)c * NS + i) * NT + tid];
         const int Ea_c = ea_s[c];
-#pragma unroll 1
-        for (int tt = 0; tt < n; ++tt) {
-            alpha_step(a, ptab + tt * PST, par);
+#pragma unroll
+        for (int tt = 0; tt < K; ++tt) {
+            if (tt >= n) break;
+            alpha_step(a, tt, par);
 #pragma unroll
             for (int i = 0; i < NS; ++i) acol[(tt * NS + i) * NT + tid] = a[i];
         }
         // posterior scale of this chunk: 2^(Ea_c + Eb - Ea_fin) / Z^
         const double sc = scalbn(inv_z, Ea_c + Eb - Ea_fin);
 
-        // -- beta over the chunk, gradient rows --
-        // boundary values for the first step of the chunk
-        if (W > 1) {
+        // -- beta over the chunk; alpha columns are overwritten by alpha*beta (own entries only) --
+        if (W > 1) {                                        // boundary values for the first step
             __syncthreads();
-            if (lane == 0) { xch[(gpar * W + warp) * 2] = bt[0]; xch[(gpar * W + warp) * 2 + 1] = bt[1]; }
+            if (lane == 0) { xch[(bpar * W + warp) * 2] = bt[0]; xch[(bpar * W + warp) * 2 + 1] = bt[1]; }
             __syncthreads();
         }
-#pragma unroll 1
-        for (int tt = n - 1; tt >= 0; --tt) {
-            const double *prow = ptab + tt * PST;
-            double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);
-            if (lane == 31) {
-                if (W > 1 && warp < W - 1) {
-                    dn0 = xch[(gpar * W + warp + 1) * 2];
-                    dn1 = xch[(gpar * W + warp + 1) * 2 + 1];
-                } else { dn0 = 0.0; dn1 = 0.0; }
-            }
-            const double pb = prow[blank];
-            double bsum = 0.0;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                const double av = acol[(tt * NS + i) * NT + tid];
-                if (i & 1) {
-                    const int jj = i >> 1;
-                    const double pl = *(const double *)((const char *)prow + poff[jj]);
-                    double s = bt[i] + ((i + 1 < NS) ? bt[i + 1] : dn0);
-                    const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
-                    if ((mbits >> (jj + 1)) & 1u) s += n2;
-                    bt[i] = s * pl;
-                    gam[gpar * LP + j0 + jj] = av * bt[i];
-                } else {
-                    const double s = bt[i] + bt[i + 1];
-                    bt[i] = s * pb;
-                    bsum = fma(av, bt[i], bsum);
+        for (int tt = K - 1; tt >= 0; --tt) {
+            if (tt < n) {
+                double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);
+                if (lane == 31) {
+                    if (W > 1 && warp < W - 1) {
+                        dn0 = xch[(bpar * W + warp + 1) * 2];
+                        dn1 = xch[(bpar * W + warp + 1) * 2 + 1];
+                    } else { dn0 = 0.0; dn1 = 0.0; }
                 }
-            }
-            // blank posterior (already divided by nothing: p~ division happens in the gather)
-            float bp = (float)(bsum * sc);
+                const double pb = *(const double *)(smem + pboff + tt * 8);
+                double bsum = 0.0;
 #pragma unroll
-            for (int o = 16; o >= 1; o >>= 1) bp += __shfl_xor_sync(0xffffffffu, bp, o);
-            if (W > 1) {
-                if (lane == 0) {
-                    bpart[gpar * W + warp] = bp;
-                    xch[((gpar ^ 1) * W + warp) * 2] = bt[0];
-                    xch[((gpar ^ 1) * W + warp) * 2 + 1] = bt[1];
-                }
-                __syncthreads();
-            } else {
-                __syncwarp();
-            }
-            // gather: thread k sums alpha*beta over the positions of symbol k, writes grad[t, b, k]
-            {
-                const float ri = rinv[tt];
-                float *grow = grads_b + (long long)(t0 + tt) * gst;
-                float psum = 0.f;
-                for (int k = tid; k < V; k += NT) {
-                    float num;
-                    if (k == blank) {
-                        if (W > 1) {
-                            num = 0.f;
-#pragma unroll
-                            for (int w = 0; w < W; ++w) num += bpart[gpar * W + w];
-                        } else num = bp;
+                for (int i = 0; i < NS; ++i) {
+                    double *ap = acol + (tt * NS + i) * NT + tid;
+                    const double av = *ap;
+                    if (i & 1) {
+                        const int jj = i >> 1;
+                        const double pl = *(const double *)(smem + poff[jj] + tt * 8);
+                        const double n1 = (i + 1 < NS) ? bt[i + 1] : dn0;
+                        const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
+                        bt[i] = fma(msk[jj + 1], n2, bt[i] + n1) * pl;
+                        *ap = av * bt[i];
                     } else {
-                        double acc = 0.0;
-                        const int q1 = off_s[k + 1];
-                        for (int q = off_s[k]; q < q1; ++q) acc += gam[gpar * LP + pos_s[q]];
-                        num = (float)(acc * sc);
+                        bt[i] = (bt[i] + bt[i + 1]) * pb;
+                        bsum = fma(av, bt[i], bsum);
                     }
-                    const float pk = (float)prow[k];
-                    const float post = (pk > 0.f) ? __fdividef(num, pk) : 0.f;
-                    psum += post;
-                    grow[k] = (pk * ri - post) * P.grad_scale;
                 }
-                // self-check once per chunk: the posteriors of a frame must sum to 1
-                if (tt == 0 && z_ok) {                      // CTA-uniform condition
-                    float tot = psum;
-#pragma unroll
-                    for (int o = 16; o >= 1; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-                    if (W == 1) chk_dev = fmaxf(chk_dev, fabsf(tot - 1.f));
-                    else if (lane == 0 && tot != 0.f) atomicAdd(chk_acc, tot);
+                bpart[tt * NT + tid] = bsum;
+                if (W > 1) {
+                    if (lane == 0) {
+                        xch[((bpar ^ 1) * W + warp) * 2] = bt[0];
+                        xch[((bpar ^ 1) * W + warp) * 2 + 1] = bt[1];
+                    }
+                    __syncthreads();
+                    bpar ^= 1;
                 }
             }
-            gpar ^= 1;
+        }
+        cta_sync<W>();                                      // products and blank partials visible
+
+        // -- blank totals: btot[tt] = sum over threads of bpart[tt][*] --
+        {
+            const int tt = tid / RB, q = tid % RB;
+            double s = 0.0;
+            if (tt < K)
+                for (int x = q; x < NT; x += RB) s += bpart[tt * NT + x];
+#pragma unroll
+            for (int o = RB / 2; o >= 1; o >>= 1) s += shfl_xor_d(s, o);
+            if (tt < K && q == 0) btot[tt] = s;
+        }
+        cta_sync<W>();
+
+        // -- gather: item (k, group) sums alpha*beta over the positions of symbol k for TG timesteps --
+        float psum0 = 0.f;                                  // posterior mass of frame tt = 0 (self-check)
+        for (int item = tid; item < V * NG; item += NT) {
+            const int k = item / NG, tt0 = (item % NG) * TG;
+            double acc[TG];
+            if (k == blank) {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) acc[u] = btot[tt0 + u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) acc[u] = 0.0;
+                const int q1 = off_s[k + 1];
+                for (int q = off_s[k]; q < q1; ++q) {
+                    const double *gp = acol + tt0 * (NS * NT) + pos_s[q];
+#pragma unroll
+                    for (int u = 0; u < TG; ++u) acc[u] += gp[u * (NS * NT)];
+                }
+            }
+            const double *pk = ptab + k * KP + tt0;
+#pragma unroll
+            for (int u = 0; u < TG; ++u) {
+                const int tt = tt0 + u;
+                if (tt < n) {
+                    const float pt = (float)pk[u];
+                    const float num = (float)(acc[u] * sc);
+                    const float post = (pt > 0.f) ? __fdividef(num, pt) : 0.f;
+                    if (tt == 0) psum0 += post;
+                    grads_b[(long long)(t0 + tt) * gst + k] = (pt * rinv[tt] - post) * P.grad_scale;
+                }
+            }
+        }
+        // self-check once per chunk: the posteriors of a frame must sum to 1
+        if (z_ok) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) psum0 += __shfl_xor_sync(0xffffffffu, psum0, o);
+            if (W == 1) chk_dev = fmaxf(chk_dev, fabsf(psum0 - 1.f));
+            else if (lane == 0 && psum0 != 0.f) atomicAdd(chk_acc, psum0);
         }
         rescale<NS, W>(bt, Eb, scratch, warp, lane);       // (contains the barriers that order chk_acc)
         if (W > 1 && tid == 0 && z_ok) {
@@ -561,6 +594,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             chk_dev = fmaxf(chk_dev, (tot == tot) ? fabsf(tot - 1.f) : INFINITY);
             *chk_acc = 0.f;
         }
+        cta_sync<W>();                                      // gather reads of acol/ptab done before next chunk
     }
 
     if (!(chk_dev <= 1e-3f)) ustat |= UTT_RANGE;

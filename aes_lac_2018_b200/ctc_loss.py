@@ -88,7 +88,8 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         call.workspace_bytes = need.value
         call.stream = torch.cuda.current_stream(acts_d.device).cuda_stream
         call.debug_device = debug.data_ptr() if debug is not None else None
-        call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY}[mode]
+        call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY,
+                      "throughput8": _lib.FLAG_MODE_THROUGHPUT_K8}[mode]
         st = lib.ctc_b200_compute(ctypes.byref(call))
         if st != _lib.CTC_STATUS_SUCCESS:
             raise RuntimeError("ctc_b200_compute: " + _lib.status_string(lib, st))

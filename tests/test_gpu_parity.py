@@ -39,7 +39,7 @@ def _assert_close(costs, grads, ref_costs, ref_grads, tag=""):
                                       f"per-utt max {d.max(axis=(0, 2))}")
 
 
-@pytest.mark.parametrize("mode", ["throughput", "latency"])
+@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency"])
 @pytest.mark.parametrize("case", KNOWN, ids=[c["name"] for c in KNOWN])
 def test_known_answers(case, mode):
     from oracle import ctc_f64
@@ -57,7 +57,7 @@ def test_known_answers(case, mode):
     _assert_close(costs, grads, oc, og, case["name"])
 
 
-@pytest.mark.parametrize("mode", ["throughput", "latency"])
+@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency"])
 @pytest.mark.parametrize("name", sorted(TORCH_CASES))
 def test_golden_torch_f64(name, mode):
     c = TORCH_CASES[name]
@@ -78,7 +78,7 @@ SYNTH = {
 }
 
 
-@pytest.mark.parametrize("mode", ["throughput", "latency"])
+@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency"])
 @pytest.mark.parametrize("name", sorted(SYNTH))
 def test_synthetic_vs_f64_oracle(name, mode):
     from oracle import ctc_f64
@@ -99,7 +99,7 @@ def test_edge_cases_batch():
     al = np.array([24, 10, 11, 12, 8, 1, 1, 20], np.int32)
     labels = np.concatenate([np.full(18, 3), rng.integers(1, V, 9), [4], rng.integers(1, V, 5)]).astype(np.int32)
     acts = rng.standard_normal((T, len(ll), V)).astype(np.float32)
-    for mode in ("throughput", "latency"):
+    for mode in ("throughput", "throughput8", "latency"):
         costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
         oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
         _assert_close(costs, grads, oc, og, "edge/" + mode)

@@ -94,10 +94,10 @@ def main():
     for name, B, T, V, lmin, lmax in cfgs:
         acts, labels, al, ll = problem(B, T, V, lmin, lmax)
         dbg = torch.zeros(B, 4, dtype=torch.int64, device="cuda")
-        for mode in ("throughput", "latency"):
+        for mode in ("throughput", "throughput8", "latency"):
             if mode == "latency" and B > 1024:
                 continue
-            for want_grad in (True, False):
+            for want_grad in ((True, False) if mode != "throughput8" else (True,)):
                 try:
                     warm_gpu(0.2)
                     with ClockSampler() as cs:
