@@ -65,7 +65,7 @@ struct FusedParams {
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
 struct SmemLayout {
     int off_ptab, off_acol, off_bpart, off_btot, off_xch, off_zfin, off_raw, off_rinv, off_ea,
-        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, total;
+        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, int T_max)
@@ -89,6 +89,7 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_off = o;   o += (V + 1) * 4;
     l.off_misc = o;  o += 8 * 4;
     l.off_scr = o;   o += 32 * 4;
+    l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT]
     l.total = (o + 15) & ~15;
     return l;
 }
@@ -119,23 +120,30 @@ __device__ __forceinline__ float ex2_approx(float x)
 __device__ __forceinline__ double exp_wide(float d)
 {
     const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.925963033500011e-8f;
+    const bool tiny = (d < -700.f);                         // below fp64-safe range: exactly 0 (like an underflow)
     const bool is_nan = !(d == d);                          // NaN activations must poison the cost, not vanish
-    d = fmaxf(d, -800.f);
     const float yh = d * L2E_HI;
     const float yl = fmaf(d, L2E_LO, fmaf(d, L2E_HI, -yh));
     const float MAGIC = 12582912.f;                         // 1.5 * 2^23
     const float t = yh + MAGIC;
     const float yi = t - MAGIC;                             // nearest integer to yh
     const float fr = (yh - yi) + yl;                        // [-0.5, 0.5]
-    const double m = (double)ex2_approx(fr);                // [0.707, 1.415]
-    const int e = __float_as_int(t) - 0x4B400000;           // integer part (<= 0)
-    const double r = __hiloint2double(__double2hiint(m) + e * (1 << 20), __double2loint(m));
-    return is_nan ? (double)NAN : ((e < -1000) ? 0.0 : r);
+    const float mf = tiny ? 0.f : ex2_approx(fr);           // [0.707, 1.415] or 0
+    const double m = (double)mf;
+    const int e = tiny ? 0 : (__float_as_int(t) - 0x4B400000);      // integer part (<= 0)
+    int hi = __double2hiint(m) + e * (1 << 20);
+    hi = is_nan ? 0x7ff80000 : hi;
+    return __hiloint2double(hi, __double2loint(m));
 }
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -217,6 +225,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     int *misc = (int *)(smem + lay.off_misc);               // [0] repeats, [1] bad label
     float *chk_acc = (float *)(misc + 4);                   // sum_k posterior of the checked frame (W > 1)
     unsigned *scratch = (unsigned *)(smem + lay.off_scr);   // [W] cross-warp max
+    double *cks = (double *)(smem + lay.off_cks);           // [NS][NT] checkpoint column staged by cp.async
 
     const int b = P.utt_ids[blockIdx.x];
     long long dbg_c0 = 0, dbg_n0 = 0, dbg_c1 = 0;
@@ -311,11 +320,22 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     // raw-activation prefetch of chunk c into buffer c&1 (rows spread over warps, k over lanes)
     auto prefetch = [&](int c) {
         const int t0 = c * K, n = min(K, T - t0);
-        float *dst = raw + (c & 1) * K * V;
+        float *dst = raw + (c & 1) * K * V + warp * V;
+        const float *src = acts_b + (long long)(t0 + warp) * P.act_stride_t;
+        const long long rstep = (long long)W * P.act_stride_t;
+#pragma unroll 1
         for (int r = warp; r < n; r += W) {
-            const float *src = acts_b + (long long)(t0 + r) * P.act_stride_t;
-            for (int k = lane; k < V; k += 32) cp_async4(dst + r * V + k, src + k);
+#pragma unroll 1
+            for (int k = lane; k < V; k += 32) cp_async4(dst + k, src + k);
+            dst += W * V;
+            src += rstep;
         }
+        cp_async_commit();
+    };
+    // checkpoint column of chunk c -> shared staging (this thread's own NS values)
+    auto fetch_ckpt = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) cp_async8(cks + i * NT + tid, ck + ((long long)c * NS + i) * NT + tid);
         cp_async_commit();
     };
 
@@ -408,6 +428,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         }
     }
     logsum += (double)logsum_f;
+    if (want_grad) fetch_ckpt(nC - 1);                      // lands while Z^ and the cost are formed
 
     // Z^ = alpha^_{T-1}(S-1) + alpha^_{T-1}(S-2)
 #pragma unroll
@@ -468,18 +489,16 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 
     for (int c = nC - 1; c >= 0; --c) {
         const int t0 = c * K, n = min(K, T - t0);
+        cp_async_wait_all();                                // raw rows of chunk c and its checkpoint column
+        cta_sync<W>();
+#pragma unroll
+        for (int i = 0; i < NS; ++i) a[i] = cks[i * NT + tid];
+        if (c >= 1) { prefetch(c - 1); fetch_ckpt(c - 1); } // (own cks entries were just consumed)
         if (c < nC - 1) {                                   // ptab still holds the last chunk after the forward sweep
-            cp_async_wait_all();
-            cta_sync<W>();
-        }
-        if (c >= 1) prefetch(c - 1);
-        if (c < nC - 1) {
             softmax_chunk(c, false);
             cta_sync<W>();
         }
         // -- recompute alpha inside the chunk from its checkpoint --
-#pragma unroll
-        for (int i = 0; i < NS; ++i) a[i] = ck[((long long)c * NS + i) * NT + tid];
         const int Ea_c = ea_s[c];
 #pragma unroll
         for (int tt = 0; tt < K; ++tt) {
@@ -569,16 +588,17 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                 }
             }
             const double *pk = ptab + k * KP + tt0;
+            float *gp = grads_b + (long long)(t0 + tt0) * gst + k;
 #pragma unroll
             for (int u = 0; u < TG; ++u) {
                 const int tt = tt0 + u;
-                if (tt < n) {
-                    const float pt = (float)pk[u];
-                    const float num = (float)(acc[u] * sc);
-                    const float post = (pt > 0.f) ? __fdividef(num, pt) : 0.f;
-                    if (tt == 0) psum0 += post;
-                    grads_b[(long long)(t0 + tt) * gst + k] = (pt * rinv[tt] - post) * P.grad_scale;
-                }
+                const float pt = (float)pk[u];
+                const float num = (float)(acc[u] * sc);
+                float post = __fdividef(num, pt);
+                post = (pt > 0.f) ? post : 0.f;
+                if (tt == 0) psum0 += post;
+                if (tt < n) *gp = (pt * rinv[tt] - post) * P.grad_scale;
+                gp += gst;
             }
         }
         // self-check once per chunk: the posteriors of a frame must sum to 1
