@@ -78,6 +78,7 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_acol = o;  o += K * SP * 8;                       // [K][NS][NT] doubles
     l.off_bpart = o; o += K * NT * 8;                       // [K][NT] doubles: per-thread blank products
     l.off_btot = o;  o += K * 8;                            // [K] doubles
+    l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT] doubles
     l.off_xch = o;   o += 2 * W * 2 * 8;
     l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
     l.off_raw = o;   o += 2 * K * V * 4;
@@ -89,7 +90,6 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_off = o;   o += (V + 1) * 4;
     l.off_misc = o;  o += 8 * 4;
     l.off_scr = o;   o += 32 * 4;
-    l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT]
     l.total = (o + 15) & ~15;
     return l;
 }
