@@ -16,12 +16,12 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libctc_b200.so")
-SOURCES = ["ctc_abi.cu"]
-HEADERS = ["ctc_fused.cuh", os.path.join(ROOT, "include", "ctc.h")]
+N_GROUPS = 6
+HEADERS = ["ctc_fused.cuh", "ctc_variants.h", "ctc_variants.cu", "ctc_abi.cu", os.path.join(ROOT, "include", "ctc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-Xptxas=-v",
+    "-Xcompiler", "-fPIC", "-Xptxas=-v",
 ]   # no --use_fast_math: fast intrinsics are chosen explicitly, per call site, in the kernels
 
 
@@ -36,26 +36,48 @@ def is_stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    deps = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(args):
+    cmd, log = args
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    return proc.returncode, " ".join(cmd), proc.stdout + proc.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the variant groups in parallel (one nvcc per group), then link libctc_b200.so."""
     if not force and not is_stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB + ".tmp"] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    # the image's $CC wrapper is not a usable host compiler for nvcc; let nvcc find the distro g++
-    proc = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    obj_dir = os.path.join(PKG, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    jobs, objs = [], []
+    for g in range(N_GROUPS):
+        o = os.path.join(obj_dir, f"ctc_variants_g{g}.o")
+        objs.append(o)
+        jobs.append(([nvcc, *NVCC_FLAGS, f"-DCTC_GROUP={g}", "-c", os.path.join(CSRC, "ctc_variants.cu"), "-o", o], None))
+    o = os.path.join(obj_dir, "ctc_abi.o")
+    objs.append(o)
+    jobs.append(([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "ctc_abi.cu"), "-o", o], None))
+    logs = []
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        for rc, cmd, out in ex.map(_compile, jobs):
+            logs.append(f"$ {cmd}\n{out}")
+            if rc != 0:
+                raise RuntimeError("nvcc failed:\n" + cmd + "\n" + out)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB + ".tmp", *objs]
+    rc, cmd, out = _compile((link, None))
+    if rc != 0:
+        raise RuntimeError("link failed:\n" + cmd + "\n" + out)
     os.replace(LIB + ".tmp", LIB)
-    log = os.path.join(LIB_DIR, "ptxas.log")
-    with open(log, "w") as f:
-        f.write(proc.stdout + proc.stderr)
+    with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
+        f.write("\n".join(logs))
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
     return LIB
 
 

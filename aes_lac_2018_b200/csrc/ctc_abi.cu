@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/ctc.h"
-#include "ctc_fused.cuh"
+#include "ctc_variants.h"
 
 namespace {
 
@@ -29,40 +29,24 @@ ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
 }
 
 // ---- kernel variants --------------------------------------------------------------------------
-// (NS states per thread, W warps per utterance, K timesteps per chunk).  SP = 32*NS*W padded states;
-// an utterance with L labels fits when SP >= 2L + 2.
-struct Variant {
-    int NS, W, K;
-    void (*kernel)(const FusedParams);
-    int max_label() const { return (32 * NS * W) / 2 - 1; }
-    int sp() const { return 32 * NS * W; }
-};
-
-#define CTC_VARIANT(NS, W, K) Variant{NS, W, K, ctc_fused_kernel<NS, W, K>}
-
-// Throughput ladder: one warp per utterance, as few states per thread as fit.
-const Variant kThroughput[] = {
-    CTC_VARIANT(2, 1, 16),  CTC_VARIANT(4, 1, 16),  CTC_VARIANT(6, 1, 16),  CTC_VARIANT(8, 1, 16),
-    CTC_VARIANT(10, 1, 16), CTC_VARIANT(12, 1, 16), CTC_VARIANT(14, 1, 16), CTC_VARIANT(16, 1, 16),
-    CTC_VARIANT(16, 2, 16), CTC_VARIANT(16, 4, 8),  CTC_VARIANT(16, 8, 4),
-};
-// Same ladder with 8-step chunks: half the shared memory per CTA (more CTAs per SM), twice the
-// checkpoint traffic and per-chunk overhead.
-const Variant kThroughput8[] = {
-    CTC_VARIANT(2, 1, 8),  CTC_VARIANT(4, 1, 8),  CTC_VARIANT(6, 1, 8),  CTC_VARIANT(8, 1, 8),
-    CTC_VARIANT(10, 1, 8), CTC_VARIANT(12, 1, 8), CTC_VARIANT(14, 1, 8), CTC_VARIANT(16, 1, 8),
-    CTC_VARIANT(16, 2, 8), CTC_VARIANT(16, 4, 8), CTC_VARIANT(16, 8, 4),
-};
-// Latency ladder (few utterances in flight): more warps per utterance, fewer states per thread.
-const Variant kLatency[] = {
-    CTC_VARIANT(2, 1, 16), CTC_VARIANT(2, 2, 16), CTC_VARIANT(2, 4, 16), CTC_VARIANT(4, 4, 16),
-    CTC_VARIANT(4, 8, 16), CTC_VARIANT(8, 8, 8),  CTC_VARIANT(16, 8, 4),
-};
-constexpr int kNumThroughput = sizeof(kThroughput) / sizeof(Variant);
-constexpr int kNumLatency = sizeof(kLatency) / sizeof(Variant);
-constexpr int kNumThroughput8 = sizeof(kThroughput8) / sizeof(Variant);
+// (NS states per thread, W warps per utterance, K timesteps per chunk, VCH 32-symbol alphabet slices).
+// SP = 32*NS*W padded states; an utterance with L labels fits when SP >= 2L + 2.
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
+
+const Variant *ladder_table(int ladder, int vch, int *n)
+{
+    switch (ladder * kMaxVch + (vch - 1)) {
+    case 0: return ctc_variants_group0(n);
+    case 1: return ctc_variants_group1(n);
+    case 2: return ctc_variants_group2(n);
+    case 3: return ctc_variants_group3(n);
+    case 4: return ctc_variants_group4(n);
+    case 5: return ctc_variants_group5(n);
+    }
+    *n = 0;
+    return nullptr;
+}
 
 const Variant *pick(const Variant *ladder, int n, int L)
 {
@@ -111,8 +95,12 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     // mode: 0 auto, 1 throughput ladder, 2 latency ladder.  Auto: with fewer utterances than ~2 per SM
     // the T-serial chain is the bound, so spend more warps per utterance.
     plan.latency = (mode == 2) || (mode == 0 && B <= 296);
-    const Variant *ladder = plan.latency ? kLatency : (mode == 3 ? kThroughput8 : kThroughput);
-    const int nl = plan.latency ? kNumLatency : (mode == 3 ? kNumThroughput8 : kNumThroughput);
+    const int vch = (V + 31) / 32;
+    if (vch > kMaxVch)
+        return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 64 is not supported by this build");
+    int nl = 0;
+    const Variant *ladder = ladder_table(plan.latency ? LADDER_LATENCY : (mode == 3 ? LADDER_THROUGHPUT_K8 : LADDER_THROUGHPUT),
+                                         vch, &nl);
 
     // bucket utterances by variant, longest first inside a bucket (tail balance)
     std::vector<std::pair<int, int>> order(B);       // (variant index, b)

@@ -59,13 +59,13 @@ struct FusedParams {
     long long ckpt_stride;            // doubles per CTA slot
     int V, T_max, B, blank;
     float grad_scale;
-    long long *debug;                 // optional [B][4]: fwd cycles, total cycles, total ns, smid
+    long long *debug;                 // optional [B][16]: fwd cycles, total cycles, total ns, smid, 12 phase counters
 };
 
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
 struct SmemLayout {
     int off_ptab, off_acol, off_bpart, off_btot, off_xch, off_zfin, off_raw, off_rinv, off_ea,
-        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, total;
+        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, off_dbg, total;
 };
 
 __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, int T_max)
@@ -79,9 +79,10 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_bpart = o; o += K * NT * 8;                       // [K][NT] doubles: per-thread blank products
     l.off_btot = o;  o += K * 8;                            // [K] doubles
     l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT] doubles
+    l.off_dbg = o;   o += 16 * 8;                           // phase cycle counters (profiling aid)
     l.off_xch = o;   o += 2 * W * 2 * 8;
     l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
-    l.off_raw = o;   o += 2 * K * V * 4;
+    l.off_raw = o;   o += K * V * 4;
     l.off_rinv = o;  o += K * 4;
     l.off_ea = o;    o += (nC + 1) * 4;
     l.off_lab = o;   o += LP * 4;
@@ -188,10 +189,12 @@ __device__ __forceinline__ void rescale(double (&x)[NS], int &E, unsigned *scrat
 // ---- the kernel ----------------------------------------------------------------------------------
 // NS states per thread, W warps per utterance, K timesteps per chunk (rescale / checkpoint / softmax /
 // gather granularity).
-template <int NS, int W, int K>
+// VCH: the alphabet fits 32*VCH symbols (one register-staged load per lane per row and 32-symbol slice).
+template <int NS, int W, int K, int VCH>
 __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 {
     static_assert(NS % 2 == 0 && NS >= 2 && NS <= 16, "NS must be even, <= 16");
+    static_assert(VCH >= 1 && VCH <= 4, "alphabet slices");
     constexpr int NT = 32 * W;                 // threads per CTA
     constexpr int SP = NS * NT;                // padded state count
     constexpr int LP = SP / 2;                 // padded label count
@@ -203,6 +206,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int TG = (K >= W) ? K / W : 1;   // timesteps per gather item
     constexpr int NG = K / TG;                 // gather items per symbol
     constexpr int RB = (NT / K) < 32 ? (NT / K) : 32;  // lanes per timestep in the blank reduction
+    constexpr int RPW = (K + W - 1) / W;       // staged rows per warp
+    constexpr int EPT = (32 * VCH + G - 1) / G;        // softmax elements per thread
     static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
 
     extern __shared__ __align__(16) unsigned char smem[];
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     double *btot = (double *)(smem + lay.off_btot);         // [K]
     double *xch = (double *)(smem + lay.off_xch);           // [2][W][2] cross-warp boundary values
     double *zfin = (double *)(smem + lay.off_zfin);         // [2] + [32] per-warp logsum
-    float *raw = (float *)(smem + lay.off_raw);             // [2][K][V] staged raw activations
+    float *raw = (float *)(smem + lay.off_raw);             // [K][V] staged raw activations
     float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum
     int *ea_s = (int *)(smem + lay.off_ea);                 // [nC] alpha exponent per chunk
     int *lab_s = (int *)(smem + lay.off_lab);               // [LP]
@@ -233,6 +238,14 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         dbg_c0 = clock64();
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_n0));
     }
+    long long *dbg_s = (long long *)(smem + lay.off_dbg);
+    long long dbg_last = dbg_c0;
+    const bool dbg_on = (P.debug != nullptr) && tid == 0;
+    if (dbg_on) for (int i = 0; i < 16; ++i) dbg_s[i] = 0;
+    // phase(i): charge the cycles since the previous mark to counter i (thread 0 only, profiling runs only)
+    auto phase = [&](int i) {
+        if (dbg_on) { const long long t = clock64(); dbg_s[i] += t - dbg_last; dbg_last = t; }
+    };
     const int T = P.act_len[b];
     const int L = P.label_len[b];
     const int S = 2 * L + 1;
@@ -317,20 +330,32 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     const int nC = (T + K - 1) / K;
     double *ck = P.ckpt + (long long)blockIdx.x * P.ckpt_stride;
 
-    // raw-activation prefetch of chunk c into buffer c&1 (rows spread over warps, k over lanes)
-    auto prefetch = [&](int c) {
+    // Raw activations of a chunk travel global -> registers -> shared: the loads of chunk c+1 are issued
+    // before the softmax and the K recursion steps of chunk c and are only consumed (stored to `raw`) at the
+    // top of the next chunk, so their latency hides behind the T-serial chain.  Lane = symbol (coalesced
+    // 4*V-byte row segments), rows spread over warps.
+    float xr[RPW][VCH];
+    auto issue_loads = [&](int c) {
         const int t0 = c * K, n = min(K, T - t0);
-        float *dst = raw + (c & 1) * K * V + warp * V;
-        const float *src = acts_b + (long long)(t0 + warp) * P.act_stride_t;
+        const float *src = acts_b + (long long)(t0 + warp) * P.act_stride_t + lane;
         const long long rstep = (long long)W * P.act_stride_t;
-#pragma unroll 1
-        for (int r = warp; r < n; r += W) {
-#pragma unroll 1
-            for (int k = lane; k < V; k += 32) cp_async4(dst + k, src + k);
-            dst += W * V;
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp + rr * W;
+#pragma unroll
+            for (int kk = 0; kk < VCH; ++kk)
+                xr[rr][kk] = (r < n && lane + 32 * kk < V) ? __ldg(src + 32 * kk) : 0.f;
             src += rstep;
         }
-        cp_async_commit();
+    };
+    auto stash_rows = [&]() {
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) {
+            const int r = warp + rr * W;
+#pragma unroll
+            for (int kk = 0; kk < VCH; ++kk)
+                if (r < K && lane + 32 * kk < V) raw[r * V + lane + 32 * kk] = xr[rr][kk];
+        }
     };
     // checkpoint column of chunk c -> shared staging (this thread's own NS values)
     auto fetch_ckpt = [&](int c) {
@@ -339,27 +364,35 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         cp_async_commit();
     };
 
-    // softmax of the staged chunk -> ptab (unnormalised p~, fp64), rinv; returns sum_r log(rowsum_r)
+    // softmax of the staged chunk -> ptab (unnormalised p~, fp64), rinv; returns sum_r log(rowsum_r).
+    // G lanes share a row; each holds EPT elements in registers so the EPT exp chains are independent.
     auto softmax_chunk = [&](int c, bool want_log) -> float {
         const int n = min(K, T - c * K);
-        const float *src = raw + (c & 1) * K * V;
         const int g = tid % G;
         float lg = 0.f;
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
             const int r = tid / G + ps * RP;
             const bool act = (r < n);
-            const float *row = src + r * V;
+            const float *row = raw + r * V;
+            float x[EPT];
             float m = -INFINITY;
-            if (act) for (int k = g; k < V; k += G) m = fmaxf(m, row[k]);
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int k = g + G * j;
+                x[j] = (act && k < V) ? row[k] : -INFINITY;
+                m = fmaxf(m, x[j]);
+            }
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (m == -INFINITY) m = 0.f;
             double s = 0.0;
-            if (act) for (int k = g; k < V; k += G) {
-                const double e = exp_wide(row[k] - m);
+#pragma unroll
+            for (int j = 0; j < EPT; ++j) {
+                const int k = g + G * j;
+                const double e = exp_wide(x[j] - m);        // x = -inf (padding) gives exactly 0
+                if (act && k < V) ptab[k * KP + r] = e;
                 s += e;
-                ptab[k * KP + r] = e;
             }
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) s += shfl_xor_d(s, o);
@@ -406,7 +439,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     float logsum_f = 0.f;
     double logsum = 0.0;
 
-    prefetch(0);
+    issue_loads(0);
+    phase(0);                                               // 0: prologue (labels, lists)
     for (int c = 0; c < nC; ++c) {
         rescale<NS, W>(a, Ea, scratch, warp, lane);
         if (want_grad) {
@@ -414,21 +448,26 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             for (int i = 0; i < NS; ++i) ck[((long long)c * NS + i) * NT + tid] = a[i];
             if (tid == 0) ea_s[c] = Ea;
         }
-        cp_async_wait_all();
-        cta_sync<W>();                                      // raw chunk visible; previous ptab readers done
-        if (c + 1 < nC) prefetch(c + 1);
+        phase(1);                                           // 1: fwd rescale + checkpoint store
+        stash_rows();                                       // (previous chunk's readers of raw/ptab are past their sync)
+        if (c + 1 < nC) issue_loads(c + 1);
+        cta_sync<W>();
+        phase(2);                                           // 2: fwd staged rows -> shared, next chunk's loads issued
+        phase(3);
         logsum_f += softmax_chunk(c, true);
         if ((c & 15) == 15) { logsum += (double)logsum_f; logsum_f = 0.f; }
         cta_sync<W>();
+        phase(4);                                           // 4: fwd softmax
         const int n = min(K, T - c * K);
 #pragma unroll
         for (int tt = 0; tt < K; ++tt) {
             if (tt >= n) break;
             alpha_step(a, tt, par);
         }
+        phase(5);                                           // 5: fwd alpha steps
     }
     logsum += (double)logsum_f;
-    if (want_grad) fetch_ckpt(nC - 1);                      // lands while Z^ and the cost are formed
+    if (want_grad) { fetch_ckpt(nC - 1); if (nC >= 2) issue_loads(nC - 2); }   // land while Z^ and the cost are formed
 
     // Z^ = alpha^_{T-1}(S-1) + alpha^_{T-1}(S-2)
 #pragma unroll
@@ -466,10 +505,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             unsigned smid;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            P.debug[b * 4 + 0] = dbg_c1 - dbg_c0;
-            P.debug[b * 4 + 1] = clock64() - dbg_c0;
-            P.debug[b * 4 + 2] = n1 - dbg_n0;
-            P.debug[b * 4 + 3] = smid;
+            P.debug[b * 16 + 0] = dbg_c1 - dbg_c0;
+            P.debug[b * 16 + 1] = clock64() - dbg_c0;
+            P.debug[b * 16 + 2] = n1 - dbg_n0;
+            P.debug[b * 16 + 3] = smid;
+            for (int i = 0; i < 12; ++i) P.debug[b * 16 + 4 + i] = dbg_s[i];
         }
     };
     if (!want_grad) {
@@ -489,15 +529,22 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 
     for (int c = nC - 1; c >= 0; --c) {
         const int t0 = c * K, n = min(K, T - t0);
-        cp_async_wait_all();                                // raw rows of chunk c and its checkpoint column
+        phase(6);                                           // 6: bwd rescale etc. of the previous iteration
+        cp_async_wait_all();                                // checkpoint column of chunk c
+        if (c < nC - 1) {                                   // rows of chunk c were loaded during the previous iteration
+            stash_rows();                                   // (chunk nC-1: ptab is still valid from the forward sweep and
+            if (c >= 1) issue_loads(c - 1);                 //  the registers hold chunk nC-2, issued before the loop)
+        }
         cta_sync<W>();
 #pragma unroll
         for (int i = 0; i < NS; ++i) a[i] = cks[i * NT + tid];
-        if (c >= 1) { prefetch(c - 1); fetch_ckpt(c - 1); } // (own cks entries were just consumed)
-        if (c < nC - 1) {                                   // ptab still holds the last chunk after the forward sweep
+        if (c >= 1) fetch_ckpt(c - 1);                      // (own cks entries were just consumed)
+        phase(7);                                           // 7: bwd staging
+        if (c < nC - 1) {
             softmax_chunk(c, false);
             cta_sync<W>();
         }
+        phase(8);                                           // 8: bwd softmax
         // -- recompute alpha inside the chunk from its checkpoint --
         const int Ea_c = ea_s[c];
 #pragma unroll
@@ -507,6 +554,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
             for (int i = 0; i < NS; ++i) acol[(tt * NS + i) * NT + tid] = a[i];
         }
+        phase(9);                                           // 9: alpha recompute
         // posterior scale of this chunk: 2^(Ea_c + Eb - Ea_fin) / Z^
         const double sc = scalbn(inv_z, Ea_c + Eb - Ea_fin);
 
@@ -556,6 +604,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             }
         }
         cta_sync<W>();                                      // products and blank partials visible
+        phase(10);                                          // 10: beta steps
 
         // -- blank totals: btot[tt] = sum over threads of bpart[tt][*] --
         {
@@ -588,19 +637,26 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                 }
             }
             const double *pk = ptab + k * KP + tt0;
-            float *gp = grads_b + (long long)(t0 + tt0) * gst + k;
+            float gout[TG];
 #pragma unroll
             for (int u = 0; u < TG; ++u) {
-                const int tt = tt0 + u;
                 const float pt = (float)pk[u];
                 const float num = (float)(acc[u] * sc);
                 float post = __fdividef(num, pt);
                 post = (pt > 0.f) ? post : 0.f;
-                if (tt == 0) psum0 += post;
-                if (tt < n) *gp = (pt * rinv[tt] - post) * P.grad_scale;
-                gp += gst;
+                if (u == 0) psum0 += (tt0 == 0) ? post : 0.f;
+                gout[u] = (pt * rinv[tt0 + u] - post) * P.grad_scale;
+            }
+            float *gp = grads_b + (long long)(t0 + tt0) * gst + k;
+            if (n == K) {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) gp[(long long)u * gst] = gout[u];
+            } else {
+#pragma unroll
+                for (int u = 0; u < TG; ++u) if (tt0 + u < n) gp[(long long)u * gst] = gout[u];
             }
         }
+        phase(11);                                          // 11: blank reduce + gather + gradient rows
         // self-check once per chunk: the posteriors of a frame must sum to 1
         if (z_ok) {
 #pragma unroll

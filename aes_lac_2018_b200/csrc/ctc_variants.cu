@@ -1,0 +1,37 @@
+// ctc_variants.cu -- instantiates one group of kernel variants (compile with -DCTC_GROUP=0..5).
+#include "ctc_variants.h"
+
+#ifndef CTC_GROUP
+#error "compile with -DCTC_GROUP=<0..5>"
+#endif
+
+namespace ctcb200 {
+
+#define CTC_LADDER (CTC_GROUP / 2)
+#define CTC_VCH (CTC_GROUP % 2 + 1)
+#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>}
+
+static const Variant kTable[] = {
+#if CTC_LADDER == 0
+    // throughput: one warp per utterance, as few states per thread as fit, 16-step chunks
+    V_(2, 1, 16), V_(4, 1, 16), V_(6, 1, 16), V_(8, 1, 16), V_(10, 1, 16), V_(12, 1, 16), V_(14, 1, 16), V_(16, 1, 16),
+    V_(16, 2, 16), V_(16, 4, 8), V_(16, 8, 4),
+#elif CTC_LADDER == 1
+    // same with 8-step chunks: half the shared memory per CTA, twice the checkpoint traffic
+    V_(2, 1, 8), V_(4, 1, 8), V_(6, 1, 8), V_(8, 1, 8), V_(10, 1, 8), V_(12, 1, 8), V_(14, 1, 8), V_(16, 1, 8),
+    V_(16, 2, 8), V_(16, 4, 8), V_(16, 8, 4),
+#else
+    // latency: more warps per utterance, fewer states per thread
+    V_(2, 1, 16), V_(2, 2, 16), V_(2, 4, 16), V_(4, 4, 16), V_(4, 8, 16), V_(8, 8, 8), V_(16, 8, 4),
+#endif
+};
+
+#define CTC_CAT2(a, b) a##b
+#define CTC_CAT(a, b) CTC_CAT2(a, b)
+const Variant *CTC_CAT(ctc_variants_group, CTC_GROUP)(int *n)
+{
+    *n = (int)(sizeof(kTable) / sizeof(Variant));
+    return kTable;
+}
+
+}  // namespace ctcb200

@@ -1,0 +1,27 @@
+// ctc_variants.h -- table of compiled instantiations of ctc_fused_kernel<NS, W, K, VCH>.
+// Each translation unit ctc_variants.cu -DCTC_GROUP=g contributes one group; the groups are compiled in
+// parallel by aes_lac_2018_b200/build.py and linked into libctc_b200.so.
+#pragma once
+#include "ctc_fused.cuh"
+
+namespace ctcb200 {
+
+struct Variant {
+    int NS, W, K, VCH;
+    void (*kernel)(const FusedParams);
+    int max_label() const { return (32 * NS * W) / 2 - 1; }   // SP = 32*NS*W states must hold 2L+2
+    int sp() const { return 32 * NS * W; }
+};
+
+enum Ladder { LADDER_THROUGHPUT = 0, LADDER_THROUGHPUT_K8 = 1, LADDER_LATENCY = 2, NUM_LADDERS = 3 };
+constexpr int kMaxVch = 2;                     // alphabets up to 64 symbols (reference: 29 and 43)
+
+// group id = ladder * kMaxVch + (VCH - 1)
+const Variant *ctc_variants_group0(int *n);
+const Variant *ctc_variants_group1(int *n);
+const Variant *ctc_variants_group2(int *n);
+const Variant *ctc_variants_group3(int *n);
+const Variant *ctc_variants_group4(int *n);
+const Variant *ctc_variants_group5(int *n);
+
+}  // namespace ctcb200

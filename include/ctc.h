@@ -136,8 +136,8 @@ typedef struct ctcB200Call {
     size_t workspace_bytes;
     CUstream stream;
     unsigned int flags;
-    long long *debug_device;    /* DEVICE [minibatch][4] or NULL: per-utterance {forward cycles, total cycles,
-                                   total ns, SM id} -- profiling aid, not part of the result */
+    long long *debug_device;    /* DEVICE [minibatch][16] or NULL: per-utterance {forward cycles, total cycles,
+                                   total ns, SM id, 12 phase cycle counters} -- profiling aid only */
 } ctcB200Call;
 
 /* per-utterance status bits (status_host) */

@@ -93,7 +93,7 @@ def main():
     warm_gpu(1.5)
     for name, B, T, V, lmin, lmax in cfgs:
         acts, labels, al, ll = problem(B, T, V, lmin, lmax)
-        dbg = torch.zeros(B, 4, dtype=torch.int64, device="cuda")
+        dbg = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
         for mode in ("throughput", "throughput8", "latency"):
             if mode == "latency" and B > 1024:
                 continue
@@ -114,7 +114,8 @@ def main():
                            fwd_cyc_per_step=round(float(d[:, 0].median()) / T, 1),
                            tot_cyc_per_step=round(float(d[:, 1].median()) / T, 1),
                            cta_us_med=round(float(d[:, 2].median()) / 1e3, 1), cta_us_max=round(float(d[:, 2].max()) / 1e3, 1),
-                           eff_mhz=round(float((d[:, 1] / d[:, 2].clamp(min=1)).median()) * 1e3))
+                           eff_mhz=round(float((d[:, 1] / d[:, 2].clamp(min=1)).median()) * 1e3),
+                           phases=[round(float(d[:, 4 + i].median()) / T, 1) for i in range(12)])
                 rows.append(row)
                 print(json.dumps(row), flush=True)
         del acts
