@@ -75,9 +75,9 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     const int nC = (T_max + K - 1) / K;
     int o = 0;
     l.off_ptab = o;  o += (V + 1) * (K + 1) * 8;          // [V+1][K+1] doubles, row V = zeros
-    l.off_acol = o;  o += K * SP * 8;                       // [K][NS][NT] doubles
-    l.off_bpart = o; o += K * NT * 8;                       // [K][NT] doubles: per-thread blank products
-    l.off_btot = o;  o += K * 8;                            // [K] doubles
+    l.off_acol = o;  o += K * SP * 4;                       // [K][NS][NT] 32-bit: alpha high words, then float products
+    l.off_bpart = o; o += K * NT * 4;                       // [K][NT] floats: per-thread blank posterior mass
+    l.off_btot = o;  o += ((K + 1) & ~1) * 4;               // [K] floats
     l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT] doubles
     l.off_dbg = o;   o += 16 * 8;                           // phase cycle counters (profiling aid)
     l.off_xch = o;   o += 2 * W * 2 * 8;
@@ -215,9 +215,12 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     const int V = P.V, blank = P.blank;
     const SmemLayout lay = make_layout(NS, W, K, V, P.T_max);
     double *ptab = (double *)(smem + lay.off_ptab);         // [V+1][KP]  p~ as doubles (symbol-major)
-    double *acol = (double *)(smem + lay.off_acol);         // [K][NS][NT] alpha columns, then alpha*beta
-    double *bpart = (double *)(smem + lay.off_bpart);       // [K][NT]   per-thread sum of blank alpha*beta
-    double *btot = (double *)(smem + lay.off_btot);         // [K]
+    // Recomputed alpha columns are kept as the HIGH 32 BITS of the double (sign, 11-bit exponent, 20 mantissa
+    // bits, rounded: relative error 2^-21 with the full fp64 range); the beta sweep overwrites each entry with
+    // the scaled product alpha*beta*sc as a float (posterior mass * p~, <= 1).
+    unsigned *acol = (unsigned *)(smem + lay.off_acol);     // [K][NS][NT]
+    float *bpart = (float *)(smem + lay.off_bpart);         // [K][NT]   per-thread blank posterior mass
+    float *btot = (float *)(smem + lay.off_btot);           // [K]
     double *xch = (double *)(smem + lay.off_xch);           // [2][W][2] cross-warp boundary values
     double *zfin = (double *)(smem + lay.off_zfin);         // [2] + [32] per-warp logsum
     float *raw = (float *)(smem + lay.off_raw);             // [K][V] staged raw activations
@@ -552,7 +555,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             if (tt >= n) break;
             alpha_step(a, tt, par);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) acol[(tt * NS + i) * NT + tid] = a[i];
+            for (int i = 0; i < NS; ++i)
+                acol[(tt * NS + i) * NT + tid] =
+                    (unsigned)__double2hiint(a[i]) + ((unsigned)__double2loint(a[i]) >> 31);
         }
         phase(9);                                           // 9: alpha recompute
         // posterior scale of this chunk: 2^(Ea_c + Eb - Ea_fin) / Z^
@@ -578,21 +583,21 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                 double bsum = 0.0;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) {
-                    double *ap = acol + (tt * NS + i) * NT + tid;
-                    const double av = *ap;
+                    unsigned *ap = acol + (tt * NS + i) * NT + tid;
+                    const double av = __hiloint2double((int)*ap, 0);
                     if (i & 1) {
                         const int jj = i >> 1;
                         const double pl = *(const double *)(smem + poff[jj] + tt * 8);
                         const double n1 = (i + 1 < NS) ? bt[i + 1] : dn0;
                         const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
                         bt[i] = fma(msk[jj + 1], n2, bt[i] + n1) * pl;
-                        *ap = av * bt[i];
+                        *ap = __float_as_uint((float)(av * bt[i] * sc));
                     } else {
                         bt[i] = (bt[i] + bt[i + 1]) * pb;
                         bsum = fma(av, bt[i], bsum);
                     }
                 }
-                bpart[tt * NT + tid] = bsum;
+                bpart[tt * NT + tid] = (float)(bsum * sc);
                 if (W > 1) {
                     if (lane == 0) {
                         xch[((bpar ^ 1) * W + warp) * 2] = bt[0];
@@ -609,29 +614,29 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         // -- blank totals: btot[tt] = sum over threads of bpart[tt][*] --
         {
             const int tt = tid / RB, q = tid % RB;
-            double s = 0.0;
+            float s = 0.f;
             if (tt < K)
                 for (int x = q; x < NT; x += RB) s += bpart[tt * NT + x];
 #pragma unroll
-            for (int o = RB / 2; o >= 1; o >>= 1) s += shfl_xor_d(s, o);
+            for (int o = RB / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (tt < K && q == 0) btot[tt] = s;
         }
         cta_sync<W>();
 
-        // -- gather: item (k, group) sums alpha*beta over the positions of symbol k for TG timesteps --
+        // -- gather: item (k, group) sums the scaled products over the positions of symbol k for TG timesteps --
         float psum0 = 0.f;                                  // posterior mass of frame tt = 0 (self-check)
         for (int item = tid; item < V * NG; item += NT) {
             const int k = item / NG, tt0 = (item % NG) * TG;
-            double acc[TG];
+            float acc[TG];
             if (k == blank) {
 #pragma unroll
                 for (int u = 0; u < TG; ++u) acc[u] = btot[tt0 + u];
             } else {
 #pragma unroll
-                for (int u = 0; u < TG; ++u) acc[u] = 0.0;
+                for (int u = 0; u < TG; ++u) acc[u] = 0.f;
                 const int q1 = off_s[k + 1];
                 for (int q = off_s[k]; q < q1; ++q) {
-                    const double *gp = acol + tt0 * (NS * NT) + pos_s[q];
+                    const float *gp = (const float *)acol + tt0 * (NS * NT) + pos_s[q];
 #pragma unroll
                     for (int u = 0; u < TG; ++u) acc[u] += gp[u * (NS * NT)];
                 }
@@ -641,8 +646,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
             for (int u = 0; u < TG; ++u) {
                 const float pt = (float)pk[u];
-                const float num = (float)(acc[u] * sc);
-                float post = __fdividef(num, pt);
+                float post = __fdividef(acc[u], pt);
                 post = (pt > 0.f) ? post : 0.f;
                 if (u == 0) psum0 += (tt0 == 0) ? post : 0.f;
                 gout[u] = (pt * rinv[tt0 + u] - post) * P.grad_scale;
