@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(PKG, "lib", "libctc_b200.so")
 CTC_STATUS_SUCCESS = 0
 CTC_GPU = 1
 FLAG_NO_SYNC = 0x1
+FLAG_SERIAL_LAUNCHES = 0x2
 FLAG_MODE_THROUGHPUT = 1 << 8
 FLAG_MODE_LATENCY = 2 << 8
 FLAG_MODE_THROUGHPUT_K8 = 3 << 8

@@ -143,6 +143,33 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     return CTC_STATUS_SUCCESS;
 }
 
+// Auxiliary streams so that the per-variant launches of one call overlap on the GPU instead of running
+// back to back (each variant's grid alone rarely fills 148 SMs).  Forked from / joined to the caller's
+// stream with events; created lazily per (thread, device).
+constexpr int kAuxStreams = 6;
+struct AuxStreams {
+    bool ready = false;
+    cudaStream_t s[kAuxStreams];
+    cudaEvent_t fork, join[kAuxStreams];
+};
+thread_local AuxStreams g_aux[16];
+
+AuxStreams *aux_streams()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    AuxStreams &a = g_aux[dev];
+    if (!a.ready) {
+        for (int i = 0; i < kAuxStreams; ++i) {
+            if (cudaStreamCreateWithFlags(&a.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        a.ready = true;
+    }
+    return &a;
+}
+
 bool check(cudaError_t e, const char *what, ctcStatus_t code, ctcStatus_t &out)
 {
     if (e == cudaSuccess) return true;
@@ -194,15 +221,33 @@ ctcStatus_t run(const ctcB200Call &c)
     P.grad_scale = c.grad_scale;
     P.debug = c.debug_device;
 
+    const bool serial = (c.flags & CTC_B200_FLAG_SERIAL_LAUNCHES) != 0;
+    AuxStreams *aux = (plan.launches.size() > 1 && !serial) ? aux_streams() : nullptr;
+    if (aux && !check(cudaEventRecord(aux->fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    int n_aux_used = 0, li = 0;
     for (const Plan::Launch &l : plan.launches) {
         P.utt_ids = d_meta + 3 * B + l.first;
         P.ckpt = (double *)(ws + plan.off_ckpt + l.ckpt_off);
         P.ckpt_stride = l.ckpt_stride;
+        cudaStream_t ls = stream;
+        if (aux && li > 0) {
+            const int j = (li - 1) % kAuxStreams;
+            ls = aux->s[j];
+            if (li - 1 < kAuxStreams) {
+                if (!check(cudaStreamWaitEvent(ls, aux->fork, 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+                n_aux_used = li;
+            }
+        }
         if (!check(cudaFuncSetAttribute(l.v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem),
                    "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-        l.v->kernel<<<l.count, 32 * l.v->W, l.smem, stream>>>(P);
+        l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);
         ++g_launches;
+        ++li;
         if (!check(cudaGetLastError(), "kernel launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    }
+    for (int j = 0; j < n_aux_used && j < kAuxStreams; ++j) {
+        if (!check(cudaEventRecord(aux->join[j], aux->s[j]), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        if (!check(cudaStreamWaitEvent(stream, aux->join[j], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     }
     if (no_sync) return CTC_STATUS_SUCCESS;
 

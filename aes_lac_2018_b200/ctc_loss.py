@@ -35,7 +35,8 @@ def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
 
 
 def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
-                 grad_scale: float = 1.0, mode: str = "auto", debug: torch.Tensor | None = None):
+                 grad_scale: float = 1.0, mode: str = "auto", debug: torch.Tensor | None = None,
+                 serial_launches: bool = False):
     """Runs the CUDA engine once.  Returns (costs[B] float32 CPU tensor, grads[T,B,V] CUDA tensor or None,
     status[B] int32 CPU tensor).  `acts` may be any T x B x V view whose last stride is 1."""
     lib = _lib.load()
@@ -90,6 +91,8 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         call.debug_device = debug.data_ptr() if debug is not None else None
         call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY,
                       "throughput8": _lib.FLAG_MODE_THROUGHPUT_K8}[mode]
+        if serial_launches:
+            call.flags |= _lib.FLAG_SERIAL_LAUNCHES
         st = lib.ctc_b200_compute(ctypes.byref(call))
         if st != _lib.CTC_STATUS_SUCCESS:
             raise RuntimeError("ctc_b200_compute: " + _lib.status_string(lib, st))

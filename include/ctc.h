@@ -115,6 +115,8 @@ ctcStatus_t get_workspace_size(const int *const label_lengths,
  * ---------------------------------------------------------------------------------------------- */
 
 #define CTC_B200_FLAG_NO_SYNC 0x1u       /* do not synchronise; costs_host/status_host must be NULL */
+#define CTC_B200_FLAG_SERIAL_LAUNCHES 0x2u /* keep every kernel on `stream` (no internal fork/join streams) */
+/* bits 8..9: variant ladder override (0 auto, 1 throughput, 2 latency, 3 throughput with 8-step chunks) */
 
 typedef struct ctcB200Call {
     const float *activations;   /* DEVICE; element (t,b,k) at t*act_stride_t + b*act_stride_b + k */

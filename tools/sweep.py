@@ -85,7 +85,7 @@ def main():
     rows = []
     cfgs = [
         ("c1", 4, 200, 29, 10, 50), ("c2", 32, 750, 29, 50, 200), ("b256", 256, 750, 29, 50, 200),
-        ("b1024", 1024, 750, 29, 50, 200), ("b4096", 4096, 750, 29, 50, 200),
+        ("b1024", 1024, 750, 29, 50, 200), ("b4096", 4096, 750, 29, 50, 200), ("b8192", 8192, 750, 29, 50, 200),
         ("c4", 1024, 1500, 29, 50, 200), ("L200", 2048, 750, 29, 200, 200), ("L60", 2048, 750, 29, 60, 60),
     ]
     if quick:
@@ -95,7 +95,7 @@ def main():
         acts, labels, al, ll = problem(B, T, V, lmin, lmax)
         dbg = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
         for mode in ("throughput", "throughput8", "latency"):
-            if mode == "latency" and B > 1024:
+            if mode == "latency" and B > 4096:
                 continue
             for want_grad in ((True, False) if mode != "throughput8" else (True,)):
                 try:
