@@ -92,14 +92,17 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     }
     plan.total_labels = off;
 
-    // mode: 0 auto, 1 throughput ladder, 2 latency ladder.  Auto: with fewer utterances than ~2 per SM
-    // the T-serial chain is the bound, so spend more warps per utterance.
-    plan.latency = (mode == 2) || (mode == 0 && B <= 296);
+    // mode: 0 auto, 1 throughput ladder (16-step chunks), 2 latency ladder, 3 throughput ladder (8-step chunks).
+    // Auto (measured on B200, T=750, L~U{50..200}; profiles/r1_sweep_*.json): below ~2000 utterances the GPU is
+    // not full with one warp per utterance, so spend more warps per utterance (latency ladder); above, occupancy
+    // is bounded by shared memory and the 8-step chunks win.
+    if (mode == 0) mode = (B < 2048) ? 2 : 3;
+    plan.latency = (mode == 2);
     const int vch = (V + 31) / 32;
     if (vch > kMaxVch)
         return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 64 is not supported by this build");
     int nl = 0;
-    const Variant *ladder = ladder_table(plan.latency ? LADDER_LATENCY : (mode == 3 ? LADDER_THROUGHPUT_K8 : LADDER_THROUGHPUT),
+    const Variant *ladder = ladder_table(mode == 2 ? LADDER_LATENCY : (mode == 3 ? LADDER_THROUGHPUT_K8 : LADDER_THROUGHPUT),
                                          vch, &nl);
 
     // bucket utterances by variant, longest first inside a bucket (tail balance)
