@@ -52,11 +52,36 @@ class CtcB200Call(ctypes.Structure):
         ("stream", ctypes.c_void_p),
         ("flags", ctypes.c_uint),
         ("debug_device", ctypes.c_void_p),
+        ("kernel_ms_host", ctypes.c_void_p),
+    ]
+
+
+class CtcB200HostCall(ctypes.Structure):
+    """struct ctcB200HostCall of include/ctc.h."""
+    _fields_ = [
+        ("activations", ctypes.c_void_p),
+        ("gradients", ctypes.c_void_p),
+        ("flat_labels", ctypes.c_void_p),
+        ("label_lengths", ctypes.c_void_p),
+        ("input_lengths", ctypes.c_void_p),
+        ("alphabet_size", ctypes.c_int),
+        ("minibatch", ctypes.c_int),
+        ("max_time", ctypes.c_int),
+        ("blank_label", ctypes.c_int),
+        ("grad_scale", ctypes.c_float),
+        ("costs_host", ctypes.c_void_p),
+        ("status_host", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", ctypes.c_size_t),
+        ("stream", ctypes.c_void_p),
+        ("n_chunks", ctypes.c_int),
+        ("flags", ctypes.c_uint),
     ]
 
 
 EXPORTS = ("get_warpctc_version", "ctcGetStatusString", "compute_ctc_loss", "get_workspace_size",
-           "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info")
+           "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info",
+           "ctc_b200_workspace_size_host", "ctc_b200_compute_host")
 
 _lib = None
 
@@ -91,6 +116,12 @@ def load() -> ctypes.CDLL:
     lib.ctc_b200_workspace_size.argtypes = [
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.POINTER(ctypes.c_size_t)]
+    lib.ctc_b200_workspace_size_host.restype = ctypes.c_int
+    lib.ctc_b200_workspace_size_host.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_size_t)]
+    lib.ctc_b200_compute_host.restype = ctypes.c_int
+    lib.ctc_b200_compute_host.argtypes = [ctypes.POINTER(CtcB200HostCall)]
     lib.ctc_b200_compute.restype = ctypes.c_int
     lib.ctc_b200_compute.argtypes = [ctypes.POINTER(CtcB200Call)]
     _lib = lib

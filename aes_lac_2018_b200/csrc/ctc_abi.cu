@@ -150,11 +150,16 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
 // back to back (each variant's grid alone rarely fills 148 SMs).  Forked from / joined to the caller's
 // stream with events; created lazily per (thread, device).
 constexpr int kAuxStreams = 6;
+constexpr int kPipeStreams = 3;
 struct AuxStreams {
     bool ready = false;
     cudaStream_t s[kAuxStreams];
     cudaEvent_t fork, join[kAuxStreams];
+    cudaStream_t pipe[kPipeStreams];           // host-buffer entry point: H2D / compute / D2H pipeline
+    cudaEvent_t pipe_fork, pipe_join[kPipeStreams];
+    cudaEvent_t t0, t1;                        // timing events (kernel_ms_host)
 };
+thread_local int *g_status_dev_override = nullptr;      // set by the host-buffer entry point around run()
 thread_local AuxStreams g_aux[16];
 
 AuxStreams *aux_streams()
@@ -168,6 +173,12 @@ AuxStreams *aux_streams()
             if (cudaEventCreateWithFlags(&a.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
         }
         if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        for (int i = 0; i < kPipeStreams; ++i) {
+            if (cudaStreamCreateWithFlags(&a.pipe[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+            if (cudaEventCreateWithFlags(&a.pipe_join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        }
+        if (cudaEventCreateWithFlags(&a.pipe_fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        if (cudaEventCreate(&a.t0) != cudaSuccess || cudaEventCreate(&a.t1) != cudaSuccess) return nullptr;
         a.ready = true;
     }
     return &a;
@@ -207,7 +218,7 @@ ctcStatus_t run(const ctcB200Call &c)
     int *d_meta = (int *)(ws + plan.off_meta);
     int *d_labels = (int *)(ws + plan.off_labels);
     float *d_costs = c.costs_device ? c.costs_device : (float *)(ws + plan.off_costs);
-    int *d_status = (int *)(ws + plan.off_status);
+    int *d_status = g_status_dev_override ? g_status_dev_override : (int *)(ws + plan.off_status);
 
     if (!check(cudaMemcpyAsync(d_meta, plan.meta.data(), sizeof(int) * 4 * (size_t)B, cudaMemcpyHostToDevice, stream),
                "H2D metadata", CTC_STATUS_MEMOPS_FAILED, st)) return st;
@@ -225,6 +236,8 @@ ctcStatus_t run(const ctcB200Call &c)
     P.debug = c.debug_device;
 
     const bool serial = (c.flags & CTC_B200_FLAG_SERIAL_LAUNCHES) != 0;
+    AuxStreams *tim = (c.kernel_ms_host && !no_sync) ? aux_streams() : nullptr;
+    if (tim && !check(cudaEventRecord(tim->t0, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     AuxStreams *aux = (plan.launches.size() > 1 && !serial) ? aux_streams() : nullptr;
     if (aux && !check(cudaEventRecord(aux->fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     int n_aux_used = 0, li = 0;
@@ -252,6 +265,7 @@ ctcStatus_t run(const ctcB200Call &c)
         if (!check(cudaEventRecord(aux->join[j], aux->s[j]), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
         if (!check(cudaStreamWaitEvent(stream, aux->join[j], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     }
+    if (tim && !check(cudaEventRecord(tim->t1, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     if (no_sync) return CTC_STATUS_SUCCESS;
 
     std::vector<int> h_status(B);
@@ -261,7 +275,126 @@ ctcStatus_t run(const ctcB200Call &c)
     if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
                "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
     if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    if (tim) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, tim->t0, tim->t1) == cudaSuccess) *c.kernel_ms_host = ms;
+    }
 
+    int any = 0;
+    for (int b = 0; b < B; ++b) any |= h_status[b];
+    if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
+    if (any & CTC_B200_UTT_BAD_LABEL)
+        return fail(CTC_STATUS_INVALID_VALUE, "a label is outside [0, alphabet_size) or equals the blank");
+    if (any & CTC_B200_UTT_RANGE)
+        return fail(CTC_STATUS_EXECUTION_FAILED,
+                    "fp64 dynamic range exhausted (forward/backward consistency check failed)");
+    return CTC_STATUS_SUCCESS;
+}
+
+
+// ---- host-buffer entry point: chunked H2D -> kernels -> D2H pipeline -----------------------------
+struct HostPlan {
+    int n_chunks = 1, n_buf = 1, Bc = 0;
+    size_t inner_ws = 0, acts_bytes = 0, off_costs = 0, off_status = 0, off_sets = 0, set_bytes = 0, total = 0;
+};
+
+ctcStatus_t make_host_plan(const int *label_lengths, const int *input_lengths, int V, int B, int T, bool want_grad,
+                           int n_chunks, HostPlan &hp)
+{
+    if (n_chunks <= 0) n_chunks = (B >= 2048) ? 8 : (B >= 256 ? 4 : 1);
+    n_chunks = std::max(1, std::min(n_chunks, B));
+    hp.n_chunks = n_chunks;
+    hp.Bc = (B + n_chunks - 1) / n_chunks;
+    hp.n_chunks = (B + hp.Bc - 1) / hp.Bc;
+    hp.n_buf = std::min(hp.n_chunks, kPipeStreams);
+    for (int c = 0; c < hp.n_chunks; ++c) {
+        const int lo = c * hp.Bc, n = std::min(hp.Bc, B - lo);
+        size_t need = 0;
+        ctcStatus_t st = ctc_b200_workspace_size(label_lengths + lo, input_lengths + lo, V, n, T, want_grad, &need);
+        if (st != CTC_STATUS_SUCCESS) return st;
+        hp.inner_ws = std::max(hp.inner_ws, need);
+    }
+    hp.acts_bytes = align_up(sizeof(float) * (size_t)T * hp.Bc * V, 256);
+    size_t o = 0;
+    hp.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
+    hp.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
+    hp.off_sets = o;
+    hp.set_bytes = hp.acts_bytes * (want_grad ? 2 : 1) + align_up(hp.inner_ws, 256);
+    hp.total = o + hp.set_bytes * hp.n_buf + 256;
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t run_host(const ctcB200HostCall &c)
+{
+    if (!c.activations || !c.flat_labels || !c.label_lengths || !c.input_lengths || !c.workspace || !c.costs_host)
+        return fail(CTC_STATUS_INVALID_VALUE, "null pointer argument");
+    if (c.alphabet_size <= 0 || c.minibatch <= 0 || c.max_time <= 0)
+        return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
+    const int B = c.minibatch, V = c.alphabet_size, T = c.max_time;
+    const bool want_grad = c.gradients != nullptr;
+    HostPlan hp;
+    ctcStatus_t st = make_host_plan(c.label_lengths, c.input_lengths, V, B, T, want_grad, c.n_chunks, hp);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    if (hp.total > c.workspace_bytes) return fail(CTC_STATUS_INVALID_VALUE, "workspace too small");
+    AuxStreams *aux = aux_streams();
+    if (!aux) return fail(CTC_STATUS_EXECUTION_FAILED, "could not create internal streams");
+    cudaStream_t stream = (cudaStream_t)c.stream;
+    char *ws = (char *)c.workspace;
+    float *d_costs = (float *)(ws + hp.off_costs);
+    int *d_status = (int *)(ws + hp.off_status);
+    std::vector<long long> lab_off(hp.n_chunks + 1, 0);
+    for (int ch = 0; ch < hp.n_chunks; ++ch) {
+        long long s = 0;
+        const int lo = ch * hp.Bc, n = std::min(hp.Bc, B - lo);
+        for (int b = 0; b < n; ++b) s += c.label_lengths[lo + b];
+        lab_off[ch + 1] = lab_off[ch] + s;
+    }
+    if (!check(cudaEventRecord(aux->pipe_fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    for (int i = 0; i < hp.n_buf; ++i)
+        if (!check(cudaStreamWaitEvent(aux->pipe[i], aux->pipe_fork, 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    const size_t row_all = sizeof(float) * (size_t)B * V;
+    for (int ch = 0; ch < hp.n_chunks; ++ch) {
+        const int lo = ch * hp.Bc, n = std::min(hp.Bc, B - lo);
+        const int set = ch % hp.n_buf;
+        cudaStream_t ps = aux->pipe[set];
+        char *base = ws + hp.off_sets + hp.set_bytes * set;
+        float *d_acts = (float *)base;
+        float *d_grads = want_grad ? (float *)(base + hp.acts_bytes) : nullptr;
+        void *inner = base + hp.acts_bytes * (want_grad ? 2 : 1);
+        const size_t row_c = sizeof(float) * (size_t)n * V;
+        if (!check(cudaMemcpy2DAsync(d_acts, row_c, c.activations + (size_t)lo * V, row_all, row_c, T,
+                                     cudaMemcpyHostToDevice, ps), "H2D activations", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        ctcB200Call k;
+        std::memset(&k, 0, sizeof(k));
+        k.activations = d_acts; k.act_stride_t = (long long)n * V; k.act_stride_b = V;
+        k.gradients = d_grads;
+        k.flat_labels = c.flat_labels + lab_off[ch];
+        k.label_lengths = c.label_lengths + lo;
+        k.input_lengths = c.input_lengths + lo;
+        k.alphabet_size = V; k.minibatch = n; k.max_time = T; k.blank_label = c.blank_label;
+        k.grad_scale = c.grad_scale;
+        k.costs_device = d_costs + lo;
+        k.workspace = inner; k.workspace_bytes = hp.inner_ws;
+        k.stream = (CUstream)ps;
+        k.flags = (c.flags & ~0xffu) | CTC_B200_FLAG_NO_SYNC;
+        g_status_dev_override = d_status + lo;
+        st = run(k);
+        g_status_dev_override = nullptr;
+        if (st != CTC_STATUS_SUCCESS) return st;
+        if (want_grad &&
+            !check(cudaMemcpy2DAsync(c.gradients + (size_t)lo * V, row_all, d_grads, row_c, row_c, T,
+                                     cudaMemcpyDeviceToHost, ps), "D2H gradients", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    }
+    for (int i = 0; i < hp.n_buf; ++i) {
+        if (!check(cudaEventRecord(aux->pipe_join[i], aux->pipe[i]), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        if (!check(cudaStreamWaitEvent(stream, aux->pipe_join[i], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    }
+    std::vector<int> h_status(B);
+    if (!check(cudaMemcpyAsync(c.costs_host, d_costs, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, stream),
+               "D2H costs", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
+               "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     int any = 0;
     for (int b = 0; b < B; ++b) any |= h_status[b];
     if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
@@ -320,6 +453,26 @@ ctcStatus_t ctc_b200_compute(const ctcB200Call *call)
 {
     if (!call) return fail(CTC_STATUS_INVALID_VALUE, "null call");
     return run(*call);
+}
+
+ctcStatus_t ctc_b200_workspace_size_host(const int *label_lengths, const int *input_lengths, int alphabet_size,
+                                         int minibatch, int max_time, int want_gradients, int n_chunks,
+                                         size_t *size_bytes)
+{
+    if (!size_bytes || !label_lengths || !input_lengths || alphabet_size <= 0 || minibatch <= 0 || max_time <= 0)
+        return fail(CTC_STATUS_INVALID_VALUE, "invalid argument");
+    HostPlan hp;
+    ctcStatus_t st = make_host_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
+                                    want_gradients != 0, n_chunks, hp);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    *size_bytes = hp.total;
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t ctc_b200_compute_host(const ctcB200HostCall *call)
+{
+    if (!call) return fail(CTC_STATUS_INVALID_VALUE, "null call");
+    return run_host(*call);
 }
 
 ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const input_lengths, int alphabet_size,

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["CTCLoss", "ctc_loss_raw"]
+__all__ = ["CTCLoss", "ctc_loss_raw", "ctc_loss_host"]
 
 
 def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -36,7 +36,7 @@ def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
 
 def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
                  grad_scale: float = 1.0, mode: str = "auto", debug: torch.Tensor | None = None,
-                 serial_launches: bool = False):
+                 serial_launches: bool = False, timing: dict | None = None):
     """Runs the CUDA engine once.  Returns (costs[B] float32 CPU tensor, grads[T,B,V] CUDA tensor or None,
     status[B] int32 CPU tensor).  `acts` may be any T x B x V view whose last stride is 1."""
     lib = _lib.load()
@@ -89,6 +89,8 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         call.workspace_bytes = need.value
         call.stream = torch.cuda.current_stream(acts_d.device).cuda_stream
         call.debug_device = debug.data_ptr() if debug is not None else None
+        kms = ctypes.c_float(0.0)
+        call.kernel_ms_host = ctypes.cast(ctypes.pointer(kms), ctypes.c_void_p) if timing is not None else None
         call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY,
                       "throughput8": _lib.FLAG_MODE_THROUGHPUT_K8}[mode]
         if serial_launches:
@@ -96,7 +98,69 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         st = lib.ctc_b200_compute(ctypes.byref(call))
         if st != _lib.CTC_STATUS_SUCCESS:
             raise RuntimeError("ctc_b200_compute: " + _lib.status_string(lib, st))
+        if timing is not None:
+            timing["kernel_ms"] = float(kms.value)
     return costs, grads, status
+
+
+_host_ws = {}
+
+
+def ctc_loss_host(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
+                  grad_scale: float = 1.0, grads_out: torch.Tensor | None = None, n_chunks: int = 0,
+                  device: int | None = None):
+    """End-to-end call with HOST buffers: `acts` is a CPU (ideally pinned) float32 T x B x V tensor; costs and
+    gradients come back in CPU tensors.  The copies are pipelined against the kernels inside libctc_b200.so
+    (ctc_b200_compute_host); the compute is the same sm_100a engine -- there is still no CPU compute path.
+    Returns (costs[B], grads[T,B,V] or None, status[B]) as CPU tensors."""
+    lib = _lib.load()
+    if acts.is_cuda:
+        raise ValueError("ctc_loss_host takes host tensors; use CTCLoss / ctc_loss_raw for CUDA tensors")
+    if not torch.cuda.is_available():
+        raise RuntimeError("aes_lac_2018_b200 needs a CUDA device; there is no CPU fallback")
+    if acts.dim() != 3 or acts.dtype != torch.float32:
+        raise TypeError("acts must be a float32 T x B x V tensor")
+    acts = acts.detach().contiguous()
+    T, B, V = acts.shape
+    labels_h = _as_host_int32(labels, "labels")
+    act_lens_h = _as_host_int32(act_lens, "act_lens")
+    label_lens_h = _as_host_int32(label_lens, "label_lens")
+    if labels_h.numel() == 0:
+        labels_h = torch.zeros(1, dtype=torch.int32)
+    dev = torch.cuda.current_device() if device is None else device
+    with torch.cuda.device(dev):
+        need = ctypes.c_size_t(0)
+        st = lib.ctc_b200_workspace_size_host(label_lens_h.data_ptr(), act_lens_h.data_ptr(), V, B, T,
+                                              1 if want_grad else 0, int(n_chunks), ctypes.byref(need))
+        if st != _lib.CTC_STATUS_SUCCESS:
+            raise RuntimeError("ctc_b200_workspace_size_host: " + _lib.status_string(lib, st))
+        ws = _host_ws.get(dev)
+        if ws is None or ws.numel() < need.value:
+            ws = _host_ws[dev] = torch.empty(need.value, dtype=torch.uint8, device=f"cuda:{dev}")
+        if want_grad and grads_out is None:
+            grads_out = torch.empty((T, B, V), dtype=torch.float32, pin_memory=True)
+        costs = torch.empty(B, dtype=torch.float32)
+        status = torch.empty(B, dtype=torch.int32)
+        call = _lib.CtcB200HostCall()
+        call.activations = acts.data_ptr()
+        call.gradients = grads_out.data_ptr() if want_grad else None
+        call.flat_labels = labels_h.data_ptr()
+        call.label_lengths = label_lens_h.data_ptr()
+        call.input_lengths = act_lens_h.data_ptr()
+        call.alphabet_size, call.minibatch, call.max_time = V, B, T
+        call.blank_label = int(blank)
+        call.grad_scale = float(grad_scale)
+        call.costs_host = costs.data_ptr()
+        call.status_host = status.data_ptr()
+        call.workspace = ws.data_ptr()
+        call.workspace_bytes = ws.numel()
+        call.stream = torch.cuda.current_stream(dev).cuda_stream
+        call.n_chunks = int(n_chunks)
+        call.flags = 0
+        st = lib.ctc_b200_compute_host(ctypes.byref(call))
+        if st != _lib.CTC_STATUS_SUCCESS:
+            raise RuntimeError("ctc_b200_compute_host: " + _lib.status_string(lib, st))
+    return costs, (grads_out if want_grad else None), status
 
 
 class _CTC(torch.autograd.Function):

@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the CTC loss-and-gradient hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): CTC fwd+bwd utterances/s at T=750, V=29.  A "step" is one forward+backward pass of
+the hot path over one batch of synthetic DeepSpeech2-shaped activations (BASELINE configs[1] shape:
+T=750, V=29, fp32, L ~ U{50..200}), `--batch` utterances per GPU (weak scaling: every rank owns its own
+shard; the only collective is the scalar NCCL loss sum).
+
+One JSON line on rank 0:
+  value     utterances/s with the activations already resident in HBM (CUDA events, max over ranks)
+  e2e       utterances/s through the host-buffer C-ABI entry point (pinned host activations in, host gradients
+            out, copies inside the timed region)
+  roofline  algorithmic bytes of the fused kernel launches / their device time vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the fp32 C/OpenMP restatement of warp-ctc's CPU path (oracle/) on this box's host cores
+`--impl reference` times that CPU restatement alone (warp-ctc itself is an absent third-party dependency of
+the reference), on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T, V, LMIN, LMAX = 750, 29, 50, 200
+METRIC = "CTC fwd+bwd utterances/s (T=750,V=29)"
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def make_problem(batch: int, seed: int):
+    """Deterministic synthetic problem: N(0,1) logits, uniform labels in [1, V-1]."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    acts = torch.randn(T, batch, V, generator=g, dtype=torch.float32)
+    label_lens = torch.randint(LMIN, LMAX + 1, (batch,), generator=g, dtype=torch.int32)
+    act_lens = torch.full((batch,), T, dtype=torch.int32)
+    labels = torch.randint(1, V, (int(label_lens.sum()),), generator=g, dtype=torch.int32)
+    return acts, labels, act_lens, label_lens
+
+
+def algorithmic_bytes(batch: int, label_lens) -> int:
+    """read acts once + write grads once + labels + two lengths + cost, per utterance."""
+    return 8 * T * V * batch + 4 * int(label_lens.sum()) + 12 * batch
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons during the timed region (NVML, ~50 ms period)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int = 0, period: float = 0.05):
+        self.samples, self.reasons, self.stop, self.max_mhz = [], set(), False, None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+        self.period = period
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop and self.nv is not None:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_run(sample_batch: int, min_seconds: float, max_reps: int, threads: int = 0):
+    """Times the fp32 C/OpenMP restatement of warp-ctc's CPU path (oracle/warpctc_cpu.c) on host cores."""
+    from oracle import warpctc_cpu
+    acts, labels, act_lens, label_lens = make_problem(sample_batch, seed=4321)
+    a, lab, al, ll = acts.numpy(), labels.numpy(), act_lens.numpy(), label_lens.numpy()
+    warpctc_cpu.ctc_batch(a[:, :8], lab[:int(ll[:8].sum())], al[:8], ll[:8], num_threads=threads)   # warm-up
+    reps, t0 = 0, time.perf_counter()
+    times = []
+    while reps < max_reps and (time.perf_counter() - t0 < min_seconds or reps < 2):
+        t1 = time.perf_counter()
+        costs, _ = warpctc_cpu.ctc_batch(a, lab, al, ll, num_threads=threads)
+        times.append(time.perf_counter() - t1)
+        reps += 1
+    best = min(times)
+    return {"utt_per_s": sample_batch / best, "reps": reps, "best_s": best, "mean_s": sum(times) / len(times),
+            "cores": warpctc_cpu.max_threads() if threads <= 0 else threads, "loss": float(costs.sum())}
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    sample = args.cpu_sample
+    steps, warm = args.steps, args.warmup
+    from oracle import warpctc_cpu
+    acts, labels, act_lens, label_lens = make_problem(sample, seed=4321)
+    a, lab, al, ll = acts.numpy(), labels.numpy(), act_lens.numpy(), label_lens.numpy()
+    cores = warpctc_cpu.max_threads()
+    for _ in range(warm):
+        warpctc_cpu.ctc_batch(a, lab, al, ll)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        warpctc_cpu.ctc_batch(a, lab, al, ll)
+    dt = time.perf_counter() - t0
+    val = sample * steps / dt
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1] shape T={T} V={V} L~U{{{LMIN}..{LMAX}}} fp32; bounded sample of "
+                               f"{sample} utterances per step on the host CPU",
+                   "batch_per_step": sample, "T": T, "V": V},
+        "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} utterances x {steps} steps, fp32 C/OpenMP restatement of warp-ctc's CPU path "
+                                   "(oracle/warpctc_cpu.c); warp-ctc itself is not installable offline"},
+        "e2e": {"value": val, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=8192, help="utterances per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=256, help="utterances per CPU-reference step")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from aes_lac_2018_b200 import _lib, ctc_loss_host, ctc_loss_raw
+    from aes_lac_2018_b200.distributed import all_reduce_loss
+
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    B = args.batch
+    acts_h, labels, act_lens, label_lens = make_problem(B, seed=1234 + rank)
+    acts = acts_h.to(dev)
+    alg_bytes = algorithmic_bytes(B, label_lens)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    loss_total = None
+
+    def step():
+        nonlocal loss_total
+        costs, grads, _ = ctc_loss_raw(acts, labels, act_lens, label_lens, want_grad=True)
+        local = costs.double().sum().to(torch.float32).reshape(1)
+        loss_total = all_reduce_loss(local)            # scalar NCCL sum over NVLink when world > 1
+        return grads
+
+    # ---- device-resident throughput (value) ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    n0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = B * world * args.steps / (ms_max * 1e-3)
+
+    # ---- kernel-only device time of the fused launches (roofline) ----
+    # CUDA events recorded by the library on the launching stream: first kernel launch of a call -> completion
+    # of the last one (the variant launches overlap on forked streams and are joined back before the end event).
+    kt = []
+    for _ in range(min(args.steps, 10)):
+        tm = {}
+        ctc_loss_raw(acts, labels, act_lens, label_lens, want_grad=True, timing=tm)
+        kt.append(tm["kernel_ms"])
+    kernel_ms = sorted(kt)[len(kt) // 2]
+
+    # ---- end to end with host buffers (e2e) ----
+    pinned = acts_h.pin_memory()
+    grads_h = torch.empty((T, B, V), dtype=torch.float32, pin_memory=True)
+    for _ in range(2):
+        ctc_loss_host(pinned, labels, act_lens, label_lens, grads_out=grads_h)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e0.record()
+    for _ in range(args.e2e_steps):
+        costs_h, _, _ = ctc_loss_host(pinned, labels, act_lens, label_lens, grads_out=grads_h)
+        local = costs_h.double().sum().to(torch.float32).reshape(1)
+        all_reduce_loss(local)
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    e2e_ms = max(e0.elapsed_time(e1), 0.0)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.e2e_steps / (float(t.item()) * 1e-3)
+    h2d = acts_h.numel() * 4 + labels.numel() * 4 + 2 * B * 4
+    d2h = grads_h.numel() * 4 + B * 4 + B * 4
+
+    # ---- BASELINE configs[1] literally (B=32): latency regime, reported beside the headline ----
+    a32_h, l32, al32, ll32 = make_problem(32, seed=99)
+    a32 = a32_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lat = []
+    for i in range(8):
+        flush.zero_()                                  # inputs are smaller than L2: flush it between calls
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        ctc_loss_raw(a32, l32, al32, ll32, want_grad=True)
+        k1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            lat.append(k0.elapsed_time(k1))
+    lat_ms = sorted(lat)[len(lat) // 2]
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch_set")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        out = {
+            "metric": METRIC, "value": value, "unit": "utterances/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1] shape (T={T}, V={V}, L~U{{{LMIN}..{LMAX}}}, fp32 activations, "
+                                   f"randn logits) at throughput batch {B} utterances per GPU",
+                       "batch_per_gpu": B, "global_batch": B * world, "T": T, "V": V, "label_len": [LMIN, LMAX],
+                       "parallelism": f"batch-sharded x{world}, scalar NCCL loss sum",
+                       "l2": f"inputs larger than L2 ({acts.numel() * 4 >> 20} MiB activations + equal gradients per GPU)"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "ctc_b200_compute_host (pinned host activations in, host gradients + costs out)",
+                    "steps": args.e2e_steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "ctc_fused_kernel<NS,1,8,1> (all variant launches of one call, overlapped on forked streams)",
+                         "algorithmic_bytes_per_call": alg_bytes, "kernel_ms_per_call": kernel_ms},
+            "configs1_b32_latency": {"ms_per_call": lat_ms, "utterances_per_s": 32 / (lat_ms * 1e-3),
+                                     "note": "BASELINE configs[1] literally (B=32): T-serial chain bound; L2 flushed between calls"},
+            "loss_check": float(loss_total.item()) if loss_total is not None else None,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_run(args.cpu_sample, min_seconds=10.0, max_reps=40)
+            out["cpu_baseline"] = {"value": cb["utt_per_s"], "unit": "utterances/s", "cores": cb["cores"], "kind": "port",
+                                   "sample": f"{args.cpu_sample} utterances of the same workload x {cb['reps']} repetitions "
+                                             f"(best {cb['best_s']:.3f} s), fp32 C/OpenMP restatement of warp-ctc's CPU path"}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,8 @@ typedef struct ctcB200Call {
     unsigned int flags;
     long long *debug_device;    /* DEVICE [minibatch][16] or NULL: per-utterance {forward cycles, total cycles,
                                    total ns, SM id, 12 phase cycle counters} -- profiling aid only */
+    float *kernel_ms_host;      /* HOST or NULL: device time (CUDA events on `stream`) from the first kernel launch of
+                                   this call to the completion of its last one; needs the blocking mode */
 } ctcB200Call;
 
 /* per-utterance status bits (status_host) */
@@ -153,6 +155,40 @@ ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_l
                                     int want_gradients, size_t *size_bytes);
 
 ctcStatus_t ctc_b200_compute(const ctcB200Call *call);
+
+/*
+ * Host-buffer entry point: activations and gradients live in HOST memory (pinned for full overlap).  The
+ * batch is cut into `n_chunks` slices along the minibatch axis and streamed through the GPU as a
+ * three-stage pipeline (H2D copy of slice i+1 | kernels of slice i | D2H copy of slice i-1) on internal
+ * streams forked from `stream`; the call blocks until costs and gradients are on the host.  This is the
+ * shape of the reference's CPU-tensor call (warpctc_pytorch cpu_ctc: host activations in, host gradients
+ * out) served by the GPU.
+ */
+typedef struct ctcB200HostCall {
+    const float *activations;   /* HOST dense [max_time][minibatch][alphabet_size] */
+    float *gradients;           /* HOST same shape, or NULL for costs only */
+    const int *flat_labels;     /* HOST */
+    const int *label_lengths;   /* HOST [minibatch] */
+    const int *input_lengths;   /* HOST [minibatch] */
+    int alphabet_size;
+    int minibatch;
+    int max_time;
+    int blank_label;
+    float grad_scale;
+    float *costs_host;          /* HOST [minibatch] */
+    int *status_host;           /* HOST [minibatch] or NULL */
+    void *workspace;            /* DEVICE, ctc_b200_workspace_size_host() bytes */
+    size_t workspace_bytes;
+    CUstream stream;
+    int n_chunks;               /* <= 0: automatic */
+    unsigned int flags;         /* ladder override bits only */
+} ctcB200HostCall;
+
+ctcStatus_t ctc_b200_workspace_size_host(const int *label_lengths, const int *input_lengths,
+                                         int alphabet_size, int minibatch, int max_time,
+                                         int want_gradients, int n_chunks, size_t *size_bytes);
+
+ctcStatus_t ctc_b200_compute_host(const ctcB200HostCall *call);
 
 /* Human-readable description of the last failure on the calling thread ("" if none). */
 const char *ctc_b200_last_error(void);

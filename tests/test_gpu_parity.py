@@ -264,3 +264,20 @@ def test_full_size_properties_c4():
         assert torch.equal(c1[0], costs[b]) and torch.equal(g1[:, 0], grads[:, b])
         oc, og = ctc_f64.ctc_batch(acts[:, b:b + 1].numpy(), lab_b.numpy(), [T], [int(ll[b])])
         _assert_close(c1.numpy().astype(np.float64), g1.cpu().numpy().astype(np.float64), oc, og, f"c4 utt {b}")
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    """ctc_b200_compute_host: pinned host activations in, host gradients out, chunked pipeline inside."""
+    from aes_lac_2018_b200 import ctc_loss_host, ctc_loss_raw
+    acts, labels, al, ll = synth_problem(41, 160, 37, 29, 0, 60, tmin=100)
+    h_acts = torch.tensor(acts).pin_memory()
+    args = [torch.tensor(x) for x in (labels, al, ll)]
+    c_dev, g_dev, _ = ctc_loss_raw(h_acts.cuda(), *args, mode="latency")
+    for n_chunks in (1, 3, 5):
+        c_host, g_host, status = ctc_loss_host(h_acts, *args, n_chunks=n_chunks)
+        assert not g_host.is_cuda and not (status & 0xC).any()
+        np.testing.assert_allclose(c_host.numpy(), c_dev.numpy(), rtol=1e-6)
+        assert (g_host - g_dev.cpu()).abs().max().item() < 2e-6
+    c_only, g_none, _ = ctc_loss_host(h_acts, *args, want_grad=False)
+    assert g_none is None
+    np.testing.assert_allclose(c_only.numpy(), c_dev.numpy(), rtol=1e-6)
