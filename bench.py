@@ -58,7 +58,7 @@ class ClockSampler:
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index: int = 0, period: float = 0.05):
+    def __init__(self, index: int = 0, period: float = 0.01):
         self.samples, self.reasons, self.stop, self.max_mhz = [], set(), False, None
         try:
             import pynvml
