@@ -100,9 +100,18 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def host_threads() -> int:
+    """All host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm overrides it)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_run(sample_batch: int, min_seconds: float, max_reps: int, threads: int = 0):
     """Times the fp32 C/OpenMP restatement of warp-ctc's CPU path (oracle/warpctc_cpu.c) on host cores."""
     from oracle import warpctc_cpu
+    threads = threads if threads > 0 else host_threads()
     acts, labels, act_lens, label_lens = make_problem(sample_batch, seed=4321)
     a, lab, al, ll = acts.numpy(), labels.numpy(), act_lens.numpy(), label_lens.numpy()
     warpctc_cpu.ctc_batch(a[:, :8], lab[:int(ll[:8].sum())], al[:8], ll[:8], num_threads=threads)   # warm-up
@@ -126,12 +135,12 @@ def run_reference(args, rank: int, world: int):
     from oracle import warpctc_cpu
     acts, labels, act_lens, label_lens = make_problem(sample, seed=4321)
     a, lab, al, ll = acts.numpy(), labels.numpy(), act_lens.numpy(), label_lens.numpy()
-    cores = warpctc_cpu.max_threads()
+    cores = host_threads()
     for _ in range(warm):
-        warpctc_cpu.ctc_batch(a, lab, al, ll)
+        warpctc_cpu.ctc_batch(a, lab, al, ll, num_threads=cores)
     t0 = time.perf_counter()
     for _ in range(steps):
-        warpctc_cpu.ctc_batch(a, lab, al, ll)
+        warpctc_cpu.ctc_batch(a, lab, al, ll, num_threads=cores)
     dt = time.perf_counter() - t0
     val = sample * steps / dt
     out = {
