@@ -132,7 +132,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         Plan::Launch l;
         l.v = v; l.first = i; l.count = j - i;
         const int nC = (T_max + v->K - 1) / v->K;
-        l.ckpt_stride = want_grad ? (long long)nC * v->sp() : 0;
+        // per CTA: nC checkpoint columns (SP doubles each) followed by nC p~ images
+        l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
         l.ckpt_off = ck;
         ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.count;
         l.smem = make_layout(v->NS, v->W, v->K, V, T_max).total;

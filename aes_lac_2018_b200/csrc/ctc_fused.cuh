@@ -65,16 +65,26 @@ struct FusedParams {
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
 struct SmemLayout {
     int off_ptab, off_acol, off_bpart, off_btot, off_xch, off_zfin, off_raw, off_rinv, off_ea,
-        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, off_dbg, total;
+        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, off_dbg, off_pstg, total;
 };
+
+// bytes of one p~ image: the [VP+1][K+1] fp64 table followed by the K fp32 reciprocal row sums, 16-byte granular
+__host__ __device__ inline int pimg_bytes(int K, int V)
+{
+    const int VP = (V + 31) / 32 * 32;
+    return ((VP + 1) * (K + 1) * 8 + K * 4 + 15) & ~15;
+}
 
 __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, int T_max)
 {
     SmemLayout l;
+    const int VP = (V + 31) / 32 * 32;
     const int NT = 32 * W, SP = NS * NT, LP = SP / 2;
     const int nC = (T_max + K - 1) / K;
     int o = 0;
-    l.off_ptab = o;  o += (V + 1) * (K + 1) * 8;          // [V+1][K+1] doubles, row V = zeros
+    l.off_ptab = o;  o += (VP + 1) * (K + 1) * 8;         // [VP+1][K+1] doubles, row VP = zeros ...
+    l.off_rinv = o;  o = l.off_ptab + pimg_bytes(K, V);     // ... immediately followed by rinv[K]: one image
+    l.off_pstg = o;  o += pimg_bytes(K, V);                 // staging copy of the previous chunk's image (backward)
     l.off_acol = o;  o += K * SP * 4;                       // [K][NS][NT] 32-bit: alpha high words, then float products
     l.off_bpart = o; o += K * NT * 4;                       // [K][NT] floats: per-thread blank posterior mass
     l.off_btot = o;  o += ((K + 1) & ~1) * 4;               // [K] floats
@@ -82,8 +92,7 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_dbg = o;   o += 16 * 8;                           // phase cycle counters (profiling aid)
     l.off_xch = o;   o += 2 * W * 2 * 8;
     l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
-    l.off_raw = o;   o += K * V * 4;
-    l.off_rinv = o;  o += K * 4;
+    l.off_raw = o;   o += K * VP * 4;                       // [K][VP] staged raw activations, pad columns = -inf
     l.off_ea = o;    o += (nC + 1) * 4;
     l.off_lab = o;   o += LP * 4;
     l.off_pos = o;   o += LP * 4;
@@ -121,8 +130,8 @@ __device__ __forceinline__ float ex2_approx(float x)
 __device__ __forceinline__ double exp_wide(float d)
 {
     const float L2E_HI = 1.44269502162933349609375f, L2E_LO = 1.925963033500011e-8f;
-    const bool tiny = (d < -700.f);                         // below fp64-safe range: exactly 0 (like an underflow)
-    const bool is_nan = !(d == d);                          // NaN activations must poison the cost, not vanish
+    const bool tiny = !(d >= -700.f);                       // below the fp64-safe range (or NaN): exactly 0;
+                                                            // NaN rows are poisoned by the caller (softmax_chunk)
     const float yh = d * L2E_HI;
     const float yl = fmaf(d, L2E_LO, fmaf(d, L2E_HI, -yh));
     const float MAGIC = 12582912.f;                         // 1.5 * 2^23
@@ -132,9 +141,7 @@ __device__ __forceinline__ double exp_wide(float d)
     const float mf = tiny ? 0.f : ex2_approx(fr);           // [0.707, 1.415] or 0
     const double m = (double)mf;
     const int e = tiny ? 0 : (__float_as_int(t) - 0x4B400000);      // integer part (<= 0)
-    int hi = __double2hiint(m) + e * (1 << 20);
-    hi = is_nan ? 0x7ff80000 : hi;
-    return __hiloint2double(hi, __double2loint(m));
+    return __hiloint2double(__double2hiint(m) + e * (1 << 20), __double2loint(m));
 }
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 {
@@ -145,6 +152,11 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
@@ -207,23 +219,25 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int NG = K / TG;                 // gather items per symbol
     constexpr int RB = (NT / K) < 32 ? (NT / K) : 32;  // lanes per timestep in the blank reduction
     constexpr int RPW = (K + W - 1) / W;       // staged rows per warp
-    constexpr int EPT = (32 * VCH + G - 1) / G;        // softmax elements per thread
+    constexpr int VP = 32 * VCH;               // padded alphabet
+    constexpr int EPT = VP / G;                // softmax elements per thread
+    static_assert(VP % G == 0, "softmax split");
     static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
 
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = P.V, blank = P.blank;
     const SmemLayout lay = make_layout(NS, W, K, V, P.T_max);
-    double *ptab = (double *)(smem + lay.off_ptab);         // [V+1][KP]  p~ as doubles (symbol-major)
+    double *ptab = (double *)(smem + lay.off_ptab);         // [VP+1][KP] p~ as doubles (symbol-major), row VP = 0
     // Recomputed alpha columns are kept as the HIGH 32 BITS of the double (sign, 11-bit exponent, 20 mantissa
-    // bits, rounded: relative error 2^-21 with the full fp64 range); the beta sweep overwrites each entry with
+    // bits, truncated and mean-corrected: relative error +-2^-21 with the full fp64 range); the beta sweep overwrites each entry with
     // the scaled product alpha*beta*sc as a float (posterior mass * p~, <= 1).
     unsigned *acol = (unsigned *)(smem + lay.off_acol);     // [K][NS][NT]
     float *bpart = (float *)(smem + lay.off_bpart);         // [K][NT]   per-thread blank posterior mass
     float *btot = (float *)(smem + lay.off_btot);           // [K]
     double *xch = (double *)(smem + lay.off_xch);           // [2][W][2] cross-warp boundary values
     double *zfin = (double *)(smem + lay.off_zfin);         // [2] + [32] per-warp logsum
-    float *raw = (float *)(smem + lay.off_raw);             // [K][V] staged raw activations
+    float *raw = (float *)(smem + lay.off_raw);             // [K][VP] staged raw activations (pad = -inf)
     float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum
     int *ea_s = (int *)(smem + lay.off_ea);                 // [nC] alpha exponent per chunk
     int *lab_s = (int *)(smem + lay.off_lab);               // [LP]
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         const int j = j0 + jj;
         const int cur = (j < LP) ? lab_s[j] : -1;
         const int prv = (j >= 1 && j - 1 < LP) ? lab_s[j - 1] : -1;
-        if (jj < NL) poff[jj] = lay.off_ptab + (cur < 0 ? V : cur) * (KP * 8);
+        if (jj < NL) poff[jj] = lay.off_ptab + (cur < 0 ? VP : cur) * (KP * 8);
         msk[jj] = (cur >= 0 && j >= 1 && cur != prv) ? 1.0 : 0.0;
     }
     const int pboff = lay.off_ptab + blank * (KP * 8);
@@ -327,11 +341,14 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     }
     if (tid < 2 * W * 2) xch[tid] = 0.0;
     if (tid < 2) zfin[tid] = 0.0;
-    for (int i = tid; i < KP; i += NT) ptab[V * KP + i] = 0.0;       // the "no label here" row
+    for (int i = tid; i < KP; i += NT) ptab[VP * KP + i] = 0.0;      // the "no label here" row
+    for (int i = tid; i < K * VP; i += NT) raw[i] = -INFINITY;       // pad columns stay -inf (p~ = 0)
     __syncthreads();
 
     const int nC = (T + K - 1) / K;
     double *ck = P.ckpt + (long long)blockIdx.x * P.ckpt_stride;
+    const int IMG = pimg_bytes(K, V);                       // bytes of one p~ image
+    char *pimg = (char *)(ck + (long long)((P.T_max + K - 1) / K) * SP);   // images follow the checkpoint columns
 
     // Raw activations of a chunk travel global -> registers -> shared: the loads of chunk c+1 are issued
     // before the softmax and the K recursion steps of chunk c and are only consumed (stored to `raw`) at the
@@ -357,7 +374,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             const int r = warp + rr * W;
 #pragma unroll
             for (int kk = 0; kk < VCH; ++kk)
-                if (r < K && lane + 32 * kk < V) raw[r * V + lane + 32 * kk] = xr[rr][kk];
+                if (r < K && lane + 32 * kk < V) raw[r * VP + lane + 32 * kk] = xr[rr][kk];
         }
     };
     // checkpoint column of chunk c -> shared staging (this thread's own NS values)
@@ -369,22 +386,25 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 
     // softmax of the staged chunk -> ptab (unnormalised p~, fp64), rinv; returns sum_r log(rowsum_r).
     // G lanes share a row; each holds EPT elements in registers so the EPT exp chains are independent.
-    auto softmax_chunk = [&](int c, bool want_log) -> float {
+    // Rows are padded to VP columns with -inf, so there are no per-element predicates (p~ of a pad column = 0
+    // lands in an unused table row).  Rows r >= n of a partial last chunk are computed on stale data and ignored.
+    auto softmax_chunk = [&](int c) -> float {
         const int n = min(K, T - c * K);
         const int g = tid % G;
         float lg = 0.f;
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
             const int r = tid / G + ps * RP;
-            const bool act = (r < n);
-            const float *row = raw + r * V;
+            const float *row = raw + r * VP + g;
+            double *pcol = ptab + g * KP + r;
             float x[EPT];
             float m = -INFINITY;
+            bool bad = false;
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
-                const int k = g + G * j;
-                x[j] = (act && k < V) ? row[k] : -INFINITY;
+                x[j] = row[G * j];
                 m = fmaxf(m, x[j]);
+                bad |= (x[j] != x[j]);
             }
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -392,20 +412,39 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
-                const int k = g + G * j;
                 const double e = exp_wide(x[j] - m);        // x = -inf (padding) gives exactly 0
-                if (act && k < V) ptab[k * KP + r] = e;
+                pcol[j * (G * KP)] = e;
                 s += e;
             }
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) s += shfl_xor_d(s, o);
-            if (act && g == 0) {
-                const float sf = (float)s;                  // in [1, V]
-                rinv[r] = (sf > 0.f) ? 1.f / sf : 0.f;
-                if (want_log) lg += __logf(sf);
+#pragma unroll
+            for (int o = G / 2; o >= 1; o >>= 1) bad |= (__shfl_xor_sync(0xffffffffu, (int)bad, o) != 0);
+            if (g == 0 && r < n) {
+                const float sf = bad ? NAN : (float)s;      // NaN activations poison the row (cost and gradient)
+                rinv[r] = (sf > 0.f) ? 1.f / sf : (bad ? NAN : 0.f);
+                lg += __logf(sf);
             }
         }
         return lg;
+    };
+    // forward: publish the finished image (table + rinv) of chunk c for the backward sweep
+    auto store_image = [&](int c) {
+        const int4 *src = (const int4 *)(smem + lay.off_ptab);
+        int4 *dst = (int4 *)(pimg + (long long)c * IMG);
+        for (int o = tid; o < IMG / 16; o += NT) dst[o] = src[o];
+    };
+    // backward: fetch the image of chunk c into the staging buffer (cp.async, consumed one chunk later)
+    auto fetch_image = [&](int c) {
+        const char *src = pimg + (long long)c * IMG;
+        unsigned char *dst = smem + lay.off_pstg;
+        for (int o = tid; o < IMG / 16; o += NT) cp_async16(dst + o * 16, src + o * 16);
+        cp_async_commit();
+    };
+    auto unstage_image = [&]() {
+        const int4 *src = (const int4 *)(smem + lay.off_pstg);
+        int4 *dst = (int4 *)(smem + lay.off_ptab);
+        for (int o = tid; o < IMG / 16; o += NT) dst[o] = src[o];
     };
 
     // one alpha step in place (descending i keeps old neighbours intact); tt is a compile-time constant
@@ -457,9 +496,10 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         cta_sync<W>();
         phase(2);                                           // 2: fwd staged rows -> shared, next chunk's loads issued
         phase(3);
-        logsum_f += softmax_chunk(c, true);
+        logsum_f += softmax_chunk(c);
         if ((c & 15) == 15) { logsum += (double)logsum_f; logsum_f = 0.f; }
         cta_sync<W>();
+        if (want_grad) store_image(c);
         phase(4);                                           // 4: fwd softmax
         const int n = min(K, T - c * K);
 #pragma unroll
@@ -470,7 +510,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         phase(5);                                           // 5: fwd alpha steps
     }
     logsum += (double)logsum_f;
-    if (want_grad) { fetch_ckpt(nC - 1); if (nC >= 2) issue_loads(nC - 2); }   // land while Z^ and the cost are formed
+    if (want_grad) { fetch_ckpt(nC - 1); if (nC >= 2) fetch_image(nC - 2); }   // land while Z^ and the cost are formed
 
     // Z^ = alpha^_{T-1}(S-1) + alpha^_{T-1}(S-2)
 #pragma unroll
@@ -533,20 +573,15 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     for (int c = nC - 1; c >= 0; --c) {
         const int t0 = c * K, n = min(K, T - t0);
         phase(6);                                           // 6: bwd rescale etc. of the previous iteration
-        cp_async_wait_all();                                // checkpoint column of chunk c
-        if (c < nC - 1) {                                   // rows of chunk c were loaded during the previous iteration
-            stash_rows();                                   // (chunk nC-1: ptab is still valid from the forward sweep and
-            if (c >= 1) issue_loads(c - 1);                 //  the registers hold chunk nC-2, issued before the loop)
-        }
-        cta_sync<W>();
+        cp_async_wait_all();                                // checkpoint column + p~ image of chunk c have landed
+        cta_sync<W>();                                      // ... for every thread; previous chunk's table readers done
+        if (c < nC - 1) unstage_image();                    // (chunk nC-1: the table is still valid from the forward sweep)
 #pragma unroll
         for (int i = 0; i < NS; ++i) a[i] = cks[i * NT + tid];
+        cta_sync<W>();                                      // table visible; staging buffer free
         if (c >= 1) fetch_ckpt(c - 1);                      // (own cks entries were just consumed)
+        if (c < nC - 1 && c >= 1) fetch_image(c - 1);       // (image nC-2 was requested before the loop)
         phase(7);                                           // 7: bwd staging
-        if (c < nC - 1) {
-            softmax_chunk(c, false);
-            cta_sync<W>();
-        }
         phase(8);                                           // 8: bwd softmax
         // -- recompute alpha inside the chunk from its checkpoint --
         const int Ea_c = ea_s[c];
@@ -555,13 +590,13 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             if (tt >= n) break;
             alpha_step(a, tt, par);
 #pragma unroll
-            for (int i = 0; i < NS; ++i)
-                acol[(tt * NS + i) * NT + tid] =
-                    (unsigned)__double2hiint(a[i]) + ((unsigned)__double2loint(a[i]) >> 31);
+            for (int i = 0; i < NS; ++i) acol[(tt * NS + i) * NT + tid] = (unsigned)__double2hiint(a[i]);
         }
         phase(9);                                           // 9: alpha recompute
         // posterior scale of this chunk: 2^(Ea_c + Eb - Ea_fin) / Z^
-        const double sc = scalbn(inv_z, Ea_c + Eb - Ea_fin);
+        // (the alpha columns above are TRUNCATED to their high words: a relative error uniform in [0, 2^-20);
+        //  the factor 1 + 2^-21 removes its mean, leaving the same +-2^-21 zero-mean error as rounding would)
+        const double sc = scalbn(inv_z * (1.0 + 4.76837158203125e-7), Ea_c + Eb - Ea_fin);
 
         // -- beta over the chunk; alpha columns are overwritten by alpha*beta (own entries only) --
         if (W > 1) {                                        // boundary values for the first step

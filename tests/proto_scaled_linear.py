@@ -18,10 +18,11 @@ TB = 256
 
 
 def _hiword_round(x):
-    """Keep sign/exponent/20 mantissa bits of a double (round to nearest), like the smem alpha column."""
+    """Keep sign/exponent/20 mantissa bits of a double (TRUNCATED; the kernel removes the mean of the
+    truncation error with a factor 1 + 2^-21 on the posterior scale), like the smem alpha column."""
     u = np.asarray(x, dtype=np.float64).view(np.uint64)
-    u = (u + np.uint64(0x80000000)) & np.uint64(0xFFFFFFFF00000000)
-    return u.view(np.float64)
+    u = u & np.uint64(0xFFFFFFFF00000000)
+    return u.view(np.float64) * (1.0 + 2.0 ** -21)
 
 
 def _rescale(v, target):
