@@ -68,11 +68,12 @@ struct SmemLayout {
         off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, off_dbg, off_pstg, total;
 };
 
-// bytes of one p~ image: the [VP+1][K+1] fp64 table followed by the K fp32 reciprocal row sums, 16-byte granular
+// bytes of one p~ image: the [VP+1][K+1] table of fp64 HIGH WORDS followed by the K fp32 reciprocal row sums,
+// 16-byte granular
 __host__ __device__ inline int pimg_bytes(int K, int V)
 {
     const int VP = (V + 31) / 32 * 32;
-    return ((VP + 1) * (K + 1) * 8 + K * 4 + 15) & ~15;
+    return ((VP + 1) * (K + 1) * 4 + K * 4 + 15) & ~15;
 }
 
 __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, int T_max)
@@ -82,9 +83,11 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     const int NT = 32 * W, SP = NS * NT, LP = SP / 2;
     const int nC = (T_max + K - 1) / K;
     int o = 0;
-    l.off_ptab = o;  o += (VP + 1) * (K + 1) * 8;         // [VP+1][K+1] doubles, row VP = zeros ...
-    l.off_rinv = o;  o = l.off_ptab + pimg_bytes(K, V);     // ... immediately followed by rinv[K]: one image
-    l.off_pstg = o;  o += pimg_bytes(K, V);                 // staging copy of the previous chunk's image (backward)
+    l.off_ptab = o;                                         // image buffer 0: [VP+1][K+1] high words (row VP = zeros)
+    l.off_rinv = o + (VP + 1) * (K + 1) * 4;                //                 + rinv[K]
+    o += pimg_bytes(K, V);
+    l.off_pstg = o;  o += pimg_bytes(K, V);                 // image buffer 1 (the backward sweep alternates)
+    o = (o + 7) & ~7;
     l.off_acol = o;  o += K * SP * 4;                       // [K][NS][NT] 32-bit: alpha high words, then float products
     l.off_bpart = o; o += K * NT * 4;                       // [K][NT] floats: per-thread blank posterior mass
     l.off_btot = o;  o += ((K + 1) & ~1) * 4;               // [K] floats
@@ -92,7 +95,7 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_dbg = o;   o += 16 * 8;                           // phase cycle counters (profiling aid)
     l.off_xch = o;   o += 2 * W * 2 * 8;
     l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
-    l.off_raw = o;   o += K * VP * 4;                       // [K][VP] staged raw activations, pad columns = -inf
+    l.off_raw = o;   o += K * (VP + 1) * 4;                 // [K][VP+1] staged raw activations, pad columns = -inf
     l.off_ea = o;    o += (nC + 1) * 4;
     l.off_lab = o;   o += LP * 4;
     l.off_pos = o;   o += LP * 4;
@@ -211,7 +214,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int SP = NS * NT;                // padded state count
     constexpr int LP = SP / 2;                 // padded label count
     constexpr int NL = NS / 2;                 // labels per thread
-    constexpr int KP = K + 1;                  // ptab row stride (doubles)
+    constexpr int VP_ = 32 * VCH;
+    constexpr int KP = K + 1;                  // ptab row stride (32-bit words; odd => symbols map to distinct banks)
+    constexpr int RS = VP_ + 1;                // raw row stride (odd => rows map to distinct banks)
     constexpr int G = (NT / K) < 32 ? (NT / K) : 32;   // lanes per softmax row
     constexpr int RP = NT / G;                 // rows per softmax pass
     constexpr int NPASS = (K + RP - 1) / RP;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int NG = K / TG;                 // gather items per symbol
     constexpr int RB = (NT / K) < 32 ? (NT / K) : 32;  // lanes per timestep in the blank reduction
     constexpr int RPW = (K + W - 1) / W;       // staged rows per warp
-    constexpr int VP = 32 * VCH;               // padded alphabet
+    constexpr int VP = VP_;                    // padded alphabet
     constexpr int EPT = VP / G;                // softmax elements per thread
     static_assert(VP % G == 0, "softmax split");
     static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
@@ -228,7 +233,10 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int V = P.V, blank = P.blank;
     const SmemLayout lay = make_layout(NS, W, K, V, P.T_max);
-    double *ptab = (double *)(smem + lay.off_ptab);         // [VP+1][KP] p~ as doubles (symbol-major), row VP = 0
+    // p~ table: symbol-major [VP+1][KP] HIGH WORDS of the fp64 value (truncated consistently everywhere it is used:
+    // rowsum, recursion, gradient -- equivalent to a +-2^-21 relative perturbation of p~), row VP = 0.
+    // Two image buffers (table + rinv); the forward sweep uses buffer 0, the backward sweep alternates.
+    unsigned *ptab = (unsigned *)(smem + lay.off_ptab);
     // Recomputed alpha columns are kept as the HIGH 32 BITS of the double (sign, 11-bit exponent, 20 mantissa
     // bits, truncated and mean-corrected: relative error +-2^-21 with the full fp64 range); the beta sweep overwrites each entry with
     // the scaled product alpha*beta*sc as a float (posterior mass * p~, <= 1).
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     double *xch = (double *)(smem + lay.off_xch);           // [2][W][2] cross-warp boundary values
     double *zfin = (double *)(smem + lay.off_zfin);         // [2] + [32] per-warp logsum
     float *raw = (float *)(smem + lay.off_raw);             // [K][VP] staged raw activations (pad = -inf)
-    float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum
+    float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum (buffer 0; re-pointed per backward chunk)
     int *ea_s = (int *)(smem + lay.off_ea);                 // [nC] alpha exponent per chunk
     int *lab_s = (int *)(smem + lay.off_lab);               // [LP]
     int *pos_s = (int *)(smem + lay.off_pos);               // [LP] acol element offsets grouped by symbol
@@ -303,17 +311,17 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 
     // ---- per-thread label constants ----
     const int j0 = tid * NL;
-    int poff[NL];                                           // byte offset of symbol row inside ptab
+    int poff[NL];                                           // byte offset of the symbol's row in the current table
     double msk[NL + 1];                                     // 1.0 if the skip INTO label j0+jj is allowed
 #pragma unroll
     for (int jj = 0; jj <= NL; ++jj) {
         const int j = j0 + jj;
         const int cur = (j < LP) ? lab_s[j] : -1;
         const int prv = (j >= 1 && j - 1 < LP) ? lab_s[j - 1] : -1;
-        if (jj < NL) poff[jj] = lay.off_ptab + (cur < 0 ? VP : cur) * (KP * 8);
+        if (jj < NL) poff[jj] = lay.off_ptab + (cur < 0 ? VP : cur) * (KP * 4);
         msk[jj] = (cur >= 0 && j >= 1 && cur != prv) ? 1.0 : 0.0;
     }
-    const int pboff = lay.off_ptab + blank * (KP * 8);
+    int pboff = lay.off_ptab + blank * (KP * 4);
 
     // ---- per-symbol position lists (deterministic, ascending); entries are acol element offsets ----
     if (want_grad) {
@@ -341,8 +349,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     }
     if (tid < 2 * W * 2) xch[tid] = 0.0;
     if (tid < 2) zfin[tid] = 0.0;
-    for (int i = tid; i < KP; i += NT) ptab[VP * KP + i] = 0.0;      // the "no label here" row
-    for (int i = tid; i < K * VP; i += NT) raw[i] = -INFINITY;       // pad columns stay -inf (p~ = 0)
+    for (int i = tid; i < KP; i += NT) {                             // the "no label here" row, both buffers
+        ptab[VP * KP + i] = 0u;
+        ((unsigned *)(smem + lay.off_pstg))[VP * KP + i] = 0u;
+    }
+    for (int i = tid; i < K * RS; i += NT) raw[i] = -INFINITY;       // pad columns stay -inf (p~ = 0)
     __syncthreads();
 
     const int nC = (T + K - 1) / K;
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             const int r = warp + rr * W;
 #pragma unroll
             for (int kk = 0; kk < VCH; ++kk)
-                if (r < K && lane + 32 * kk < V) raw[r * VP + lane + 32 * kk] = xr[rr][kk];
+                if (r < K && lane + 32 * kk < V) raw[r * RS + lane + 32 * kk] = xr[rr][kk];
         }
     };
     // checkpoint column of chunk c -> shared staging (this thread's own NS values)
@@ -395,8 +406,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
             const int r = tid / G + ps * RP;
-            const float *row = raw + r * VP + g;
-            double *pcol = ptab + g * KP + r;
+            const float *row = raw + r * RS + g;
+            unsigned *pcol = ptab + g * KP + r;
             float x[EPT];
             float m = -INFINITY;
             bool bad = false;
@@ -412,9 +423,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < EPT; ++j) {
-                const double e = exp_wide(x[j] - m);        // x = -inf (padding) gives exactly 0
-                pcol[j * (G * KP)] = e;
-                s += e;
+                const int eh = __double2hiint(exp_wide(x[j] - m));      // x = -inf (padding) gives exactly 0
+                pcol[j * (G * KP)] = (unsigned)eh;
+                s += __hiloint2double(eh, 0);               // the row sum uses the same truncated values
             }
 #pragma unroll
             for (int o = G / 2; o >= 1; o >>= 1) s += shfl_xor_d(s, o);
@@ -434,17 +445,12 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         int4 *dst = (int4 *)(pimg + (long long)c * IMG);
         for (int o = tid; o < IMG / 16; o += NT) dst[o] = src[o];
     };
-    // backward: fetch the image of chunk c into the staging buffer (cp.async, consumed one chunk later)
+    // backward: fetch the image of chunk c into its buffer ((nC-1-c) & 1) by cp.async, one chunk ahead of its use
     auto fetch_image = [&](int c) {
         const char *src = pimg + (long long)c * IMG;
-        unsigned char *dst = smem + lay.off_pstg;
+        unsigned char *dst = smem + (((nC - 1 - c) & 1) ? lay.off_pstg : lay.off_ptab);
         for (int o = tid; o < IMG / 16; o += NT) cp_async16(dst + o * 16, src + o * 16);
         cp_async_commit();
-    };
-    auto unstage_image = [&]() {
-        const int4 *src = (const int4 *)(smem + lay.off_pstg);
-        int4 *dst = (int4 *)(smem + lay.off_ptab);
-        for (int o = tid; o < IMG / 16; o += NT) dst[o] = src[o];
     };
 
     // one alpha step in place (descending i keeps old neighbours intact); tt is a compile-time constant
@@ -457,12 +463,12 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             if (lane == 0) up1 = (warp > 0) ? xch[(par * W + warp - 1) * 2] : 0.0;
             par ^= 1;
         } else if (lane == 0) up1 = 0.0;
-        const double pb = *(const double *)(smem + pboff + tt * 8);
+        const double pb = __hiloint2double(*(const int *)(smem + pboff + tt * 4), 0);
 #pragma unroll
         for (int i = NS - 1; i >= 0; --i) {
             if (i & 1) {
                 const int jj = i >> 1;
-                const double pl = *(const double *)(smem + poff[jj] + tt * 8);
+                const double pl = __hiloint2double(*(const int *)(smem + poff[jj] + tt * 4), 0);
                 const double p2 = (i >= 2) ? a[i - 2] : up1;
                 a[i] = fma(msk[jj], p2, a[i] + a[i - 1]) * pl;
             } else {
@@ -575,12 +581,19 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         phase(6);                                           // 6: bwd rescale etc. of the previous iteration
         cp_async_wait_all();                                // checkpoint column + p~ image of chunk c have landed
         cta_sync<W>();                                      // ... for every thread; previous chunk's table readers done
-        if (c < nC - 1) unstage_image();                    // (chunk nC-1: the table is still valid from the forward sweep)
+        if (c < nC - 1) {                                   // switch to the other image buffer (chunk nC-1 uses buffer 0,
+            const int d = (((nC - 1 - c) & 1) ? 1 : -1) * (lay.off_pstg - lay.off_ptab);   // still valid from the forward sweep)
+#pragma unroll
+            for (int jj = 0; jj < NL; ++jj) poff[jj] += d;
+            pboff += d;
+            ptab = (unsigned *)((unsigned char *)ptab + d);
+            rinv = (float *)((unsigned char *)rinv + d);
+        }
 #pragma unroll
         for (int i = 0; i < NS; ++i) a[i] = cks[i * NT + tid];
-        cta_sync<W>();                                      // table visible; staging buffer free
         if (c >= 1) fetch_ckpt(c - 1);                      // (own cks entries were just consumed)
-        if (c < nC - 1 && c >= 1) fetch_image(c - 1);       // (image nC-2 was requested before the loop)
+        if (c >= 1 && c < nC - 1) fetch_image(c - 1);       // into the buffer chunk c+1 no longer reads (image nC-2 was
+                                                            //  requested before the loop)
         phase(7);                                           // 7: bwd staging
         phase(8);                                           // 8: bwd softmax
         // -- recompute alpha inside the chunk from its checkpoint --
@@ -614,7 +627,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                         dn1 = xch[(bpar * W + warp + 1) * 2 + 1];
                     } else { dn0 = 0.0; dn1 = 0.0; }
                 }
-                const double pb = *(const double *)(smem + pboff + tt * 8);
+                const double pb = __hiloint2double(*(const int *)(smem + pboff + tt * 4), 0);
                 double bsum = 0.0;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) {
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                     const double av = __hiloint2double((int)*ap, 0);
                     if (i & 1) {
                         const int jj = i >> 1;
-                        const double pl = *(const double *)(smem + poff[jj] + tt * 8);
+                        const double pl = __hiloint2double(*(const int *)(smem + poff[jj] + tt * 4), 0);
                         const double n1 = (i + 1 < NS) ? bt[i + 1] : dn0;
                         const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
                         bt[i] = fma(msk[jj + 1], n2, bt[i] + n1) * pl;
@@ -676,11 +689,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                     for (int u = 0; u < TG; ++u) acc[u] += gp[u * (NS * NT)];
                 }
             }
-            const double *pk = ptab + k * KP + tt0;
+            const unsigned *pk = ptab + k * KP + tt0;
             float gout[TG];
 #pragma unroll
             for (int u = 0; u < TG; ++u) {
-                const float pt = (float)pk[u];
+                const float pt = (float)__hiloint2double((int)pk[u], 0);
                 float post = __fdividef(acc[u], pt);
                 post = (pt > 0.f) ? post : 0.f;
                 if (u == 0) psum0 += (tt0 == 0) ? post : 0.f;
