@@ -12,11 +12,12 @@ CTC_STATUS_SUCCESS = 0
 CTC_GPU = 1
 FLAG_NO_SYNC = 0x1
 FLAG_SERIAL_LAUNCHES = 0x2
+FLAG_NO_FALLBACK = 0x4
 FLAG_MODE_THROUGHPUT = 1 << 8
 FLAG_MODE_LATENCY = 2 << 8
 FLAG_MODE_THROUGHPUT_K8 = 3 << 8
 
-UTT_INFEASIBLE, UTT_INF_COST, UTT_BAD_LABEL, UTT_RANGE = 1, 2, 4, 8
+UTT_INFEASIBLE, UTT_INF_COST, UTT_BAD_LABEL, UTT_RANGE, UTT_LOGSPACE = 1, 2, 4, 8, 16
 
 
 class _OptUnion(ctypes.Union):

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/ctc.h"
+#include "ctc_logspace.cuh"
 #include "ctc_variants.h"
 
 namespace {
@@ -64,7 +65,8 @@ struct Plan {
     struct Launch { const Variant *v; int first, count; size_t ckpt_off; long long ckpt_stride; int smem; };
     std::vector<Launch> launches;
     long long total_labels = 0;
-    size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_ckpt = 0, total = 0;
+    size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_ckpt = 0, total = 0, ckpt_bytes = 0;
+    int fallback_S = 1;
 };
 
 // forced_w: 0 = automatic ladder choice; otherwise use the latency ladder entry with that W where possible
@@ -143,6 +145,10 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         plan.launches.push_back(l);
         i = j;
     }
+    // the checkpoint area doubles as the alpha store of the log-space fallback: keep room for one utterance
+    plan.fallback_S = 2 * max_L + 1;
+    ck = std::max(ck, sizeof(double) * (size_t)std::max(T_max, 1) * (size_t)plan.fallback_S);
+    plan.ckpt_bytes = ck;
     plan.total = align_up(o + ck, 256) + 256;
     return CTC_STATUS_SUCCESS;
 }
@@ -190,6 +196,48 @@ bool check(cudaError_t e, const char *what, ctcStatus_t code, ctcStatus_t &out)
     if (e == cudaSuccess) return true;
     out = fail(code, std::string(what) + ": " + cudaGetErrorString(e));
     return false;
+}
+
+constexpr unsigned kFlagForceLogspace = 0x80000000u;    // internal: skip the fused kernels, log-space for every utterance
+
+// Re-run the listed utterances with the fp64 log-space kernel (ctc_logspace.cuh).  The fused kernels of this
+// call have completed (the caller synchronised), so their checkpoint area is free: it is cut into alpha slots
+// of 8*T_max*S_max bytes and the utterances are processed in rounds of as many slots as fit.
+ctcStatus_t run_logspace_fallback(const ctcB200Call &c, const Plan &plan, const FusedParams &FP,
+                                  const std::vector<int> &todo, cudaStream_t stream)
+{
+    ctcStatus_t st = CTC_STATUS_SUCCESS;
+    const int B = c.minibatch, V = c.alphabet_size;
+    char *ws = (char *)c.workspace;
+    int S_max = 1;
+    for (int b : todo) S_max = std::max(S_max, 2 * c.label_lengths[b] + 1);
+    const size_t slot_doubles = (size_t)c.max_time * (size_t)S_max;
+    const size_t n_slots = std::min<size_t>(todo.size(), plan.ckpt_bytes / (slot_doubles * sizeof(double)));
+    if (n_slots == 0) return fail(CTC_STATUS_EXECUTION_FAILED, "workspace too small for the log-space fallback");
+    const int smem = logspace_smem_bytes(S_max, V);
+    if (smem > kMaxSmem) return fail(CTC_STATUS_UNKNOWN_ERROR, "label sequence too long for the log-space fallback");
+    if (!check(cudaFuncSetAttribute(ctc_logspace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+               "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    int *d_list = (int *)(ws + plan.off_meta) + 3 * B;          // the utt_ids area is free again
+    if (!check(cudaMemcpyAsync(d_list, todo.data(), sizeof(int) * todo.size(), cudaMemcpyHostToDevice, stream),
+               "H2D fallback list", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    LogParams L;
+    L.acts = FP.acts; L.act_stride_t = FP.act_stride_t; L.act_stride_b = FP.act_stride_b;
+    L.grads = FP.grads;
+    L.labels = FP.labels; L.label_off = FP.label_off; L.label_len = FP.label_len; L.act_len = FP.act_len;
+    L.costs = FP.costs; L.status = FP.status;
+    L.alpha_ws = (double *)(ws + plan.off_ckpt);
+    L.slot_stride = (long long)slot_doubles;
+    L.V = V; L.T_max = c.max_time; L.B = B; L.blank = c.blank_label; L.S_max = S_max;
+    L.grad_scale = c.grad_scale;
+    for (size_t done = 0; done < todo.size(); done += n_slots) {
+        const int n = (int)std::min(n_slots, todo.size() - done);
+        L.utt_list = d_list + done;
+        ctc_logspace_kernel<<<n, kLogThreads, smem, stream>>>(L);
+        ++g_launches;
+        if (!check(cudaGetLastError(), "fallback launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    }
+    return CTC_STATUS_SUCCESS;
 }
 
 ctcStatus_t run(const ctcB200Call &c)
@@ -241,8 +289,10 @@ ctcStatus_t run(const ctcB200Call &c)
     if (tim && !check(cudaEventRecord(tim->t0, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     AuxStreams *aux = (plan.launches.size() > 1 && !serial) ? aux_streams() : nullptr;
     if (aux && !check(cudaEventRecord(aux->fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    const bool force_log = (c.flags & kFlagForceLogspace) != 0;
     int n_aux_used = 0, li = 0;
     for (const Plan::Launch &l : plan.launches) {
+        if (force_log) break;
         P.utt_ids = d_meta + 3 * B + l.first;
         P.ckpt = (double *)(ws + plan.off_ckpt + l.ckpt_off);
         P.ckpt_stride = l.ckpt_stride;
@@ -281,6 +331,25 @@ ctcStatus_t run(const ctcB200Call &c)
         if (cudaEventElapsedTime(&ms, tim->t0, tim->t1) == cudaSuccess) *c.kernel_ms_host = ms;
     }
 
+    // Utterances whose column spread exceeded the fp64 range (Z^ underflowed to 0, or the forward/backward
+    // consistency check failed) are redone in log space; a genuine +inf cost simply comes back as +inf.
+    std::vector<int> todo;
+    for (int b = 0; b < B; ++b) {
+        if (force_log) { h_status[b] = 0; todo.push_back(b); }
+        else if ((h_status[b] & (CTC_B200_UTT_RANGE | CTC_B200_UTT_INF_COST)) && !(h_status[b] & CTC_B200_UTT_BAD_LABEL))
+            todo.push_back(b);
+    }
+    if (!todo.empty() && !(c.flags & CTC_B200_FLAG_NO_FALLBACK)) {
+        st = run_logspace_fallback(c, plan, P, todo, stream);
+        if (st != CTC_STATUS_SUCCESS) return st;
+        if (c.costs_host &&
+            !check(cudaMemcpyAsync(c.costs_host, d_costs, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, stream),
+                   "D2H costs", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
+                   "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        for (int b : todo) h_status[b] |= CTC_B200_UTT_LOGSPACE;
+    }
     int any = 0;
     for (int b = 0; b < B; ++b) any |= h_status[b];
     if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
@@ -288,7 +357,8 @@ ctcStatus_t run(const ctcB200Call &c)
         return fail(CTC_STATUS_INVALID_VALUE, "a label is outside [0, alphabet_size) or equals the blank");
     if (any & CTC_B200_UTT_RANGE)
         return fail(CTC_STATUS_EXECUTION_FAILED,
-                    "fp64 dynamic range exhausted (forward/backward consistency check failed)");
+                    (c.flags & CTC_B200_FLAG_NO_FALLBACK) ? "utterance outside the fp64 linear-domain range (fallback disabled)"
+                                                          : "non-finite partition function (NaN activations?)");
     return CTC_STATUS_SUCCESS;
 }
 
@@ -396,14 +466,62 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
     if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
                "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
     if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    // Out-of-range utterances: gather them into a compact device batch and run the log-space kernel on it.
+    std::vector<int> todo;
+    for (int b = 0; b < B; ++b)
+        if ((h_status[b] & (CTC_B200_UTT_RANGE | CTC_B200_UTT_INF_COST)) && !(h_status[b] & CTC_B200_UTT_BAD_LABEL))
+            todo.push_back(b);
+    for (size_t done = 0; done < todo.size() && !(c.flags & CTC_B200_FLAG_NO_FALLBACK); done += (size_t)hp.Bc) {
+        const int n = (int)std::min<size_t>((size_t)hp.Bc, todo.size() - done);
+        char *base = ws + hp.off_sets;                      // buffer set 0 (all pipeline work has completed)
+        float *d_acts = (float *)base;
+        float *d_grads = want_grad ? (float *)(base + hp.acts_bytes) : nullptr;
+        void *inner = base + hp.acts_bytes * (want_grad ? 2 : 1);
+        std::vector<int> sub_ll(n), sub_al(n), sub_status(n);
+        std::vector<int> sub_labels;
+        std::vector<float> sub_costs(n);
+        std::vector<long long> offs(B + 1, 0);
+        for (int b = 0; b < B; ++b) offs[b + 1] = offs[b] + c.label_lengths[b];
+        for (int i = 0; i < n; ++i) {
+            const int b = todo[done + i];
+            sub_ll[i] = c.label_lengths[b]; sub_al[i] = c.input_lengths[b];
+            sub_labels.insert(sub_labels.end(), c.flat_labels + offs[b], c.flat_labels + offs[b + 1]);
+            if (!check(cudaMemcpy2DAsync(d_acts + (size_t)i * V, sizeof(float) * (size_t)n * V, c.activations + (size_t)b * V,
+                                         row_all, sizeof(float) * V, T, cudaMemcpyHostToDevice, stream),
+                       "H2D activations (fallback)", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        }
+        if (sub_labels.empty()) sub_labels.push_back(0);
+        ctcB200Call k;
+        std::memset(&k, 0, sizeof(k));
+        k.activations = d_acts; k.act_stride_t = (long long)n * V; k.act_stride_b = V;
+        k.gradients = d_grads;
+        k.flat_labels = sub_labels.data(); k.label_lengths = sub_ll.data(); k.input_lengths = sub_al.data();
+        k.alphabet_size = V; k.minibatch = n; k.max_time = T; k.blank_label = c.blank_label;
+        k.grad_scale = c.grad_scale;
+        k.costs_host = sub_costs.data(); k.status_host = sub_status.data();
+        k.workspace = inner; k.workspace_bytes = hp.inner_ws;
+        k.stream = (CUstream)stream;
+        k.flags = kFlagForceLogspace;
+        st = run(k);
+        if (st != CTC_STATUS_SUCCESS) return st;
+        for (int i = 0; i < n; ++i) {
+            const int b = todo[done + i];
+            c.costs_host[b] = sub_costs[i];
+            h_status[b] = sub_status[i];
+            if (want_grad &&
+                !check(cudaMemcpy2DAsync(c.gradients + (size_t)b * V, row_all, d_grads + (size_t)i * V, sizeof(float) * (size_t)n * V,
+                                         sizeof(float) * V, T, cudaMemcpyDeviceToHost, stream),
+                       "D2H gradients (fallback)", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        }
+        if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    }
     int any = 0;
     for (int b = 0; b < B; ++b) any |= h_status[b];
     if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
     if (any & CTC_B200_UTT_BAD_LABEL)
         return fail(CTC_STATUS_INVALID_VALUE, "a label is outside [0, alphabet_size) or equals the blank");
     if (any & CTC_B200_UTT_RANGE)
-        return fail(CTC_STATUS_EXECUTION_FAILED,
-                    "fp64 dynamic range exhausted (forward/backward consistency check failed)");
+        return fail(CTC_STATUS_EXECUTION_FAILED, "non-finite partition function (NaN activations?)");
     return CTC_STATUS_SUCCESS;
 }
 

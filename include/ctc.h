@@ -116,6 +116,7 @@ ctcStatus_t get_workspace_size(const int *const label_lengths,
 
 #define CTC_B200_FLAG_NO_SYNC 0x1u       /* do not synchronise; costs_host/status_host must be NULL */
 #define CTC_B200_FLAG_SERIAL_LAUNCHES 0x2u /* keep every kernel on `stream` (no internal fork/join streams) */
+#define CTC_B200_FLAG_NO_FALLBACK 0x4u     /* report out-of-range utterances instead of re-running them in log space */
 /* bits 8..9: variant ladder override (0 auto, 1 throughput, 2 latency, 3 throughput with 8-step chunks) */
 
 typedef struct ctcB200Call {
@@ -148,7 +149,10 @@ typedef struct ctcB200Call {
 #define CTC_B200_UTT_INFEASIBLE 0x1     /* L + repeats > T (or T == 0): cost 0, gradient 0 */
 #define CTC_B200_UTT_INF_COST 0x2       /* no alignment has non-zero probability: cost = +inf */
 #define CTC_B200_UTT_BAD_LABEL 0x4      /* label out of range or equal to blank */
-#define CTC_B200_UTT_RANGE 0x8          /* fp64 dynamic range exhausted; utterance was redone in log space */
+#define CTC_B200_UTT_RANGE 0x8          /* non-finite partition function even in log space (NaN inputs), or out of range
+                                           with the fallback disabled */
+#define CTC_B200_UTT_LOGSPACE 0x10      /* the utterance exceeded the fp64 linear-domain range of the fused kernel
+                                           (or has a +inf cost) and was computed by the fp64 log-space kernel */
 
 ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_lengths,
                                     int alphabet_size, int minibatch, int max_time,

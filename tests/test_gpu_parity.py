@@ -190,6 +190,7 @@ def test_inf_cost_no_nan():
     acts[:, 0, 2] = -1e30
     costs, grads, status = _engine(acts, labels, [T], [L])
     assert np.isinf(costs[0]) and costs[0] > 0 and np.isfinite(grads).all() and status[0] & 0x2
+    np.testing.assert_allclose(grads.sum(-1), 1.0, atol=1e-5)        # gradient = softmax when no path exists
 
 
 def _opts(lib_mod, stream=0, blank=0, loc=1):
@@ -281,3 +282,41 @@ def test_host_buffer_entry_point_matches_device_path():
     c_only, g_none, _ = ctc_loss_host(h_acts, *args, want_grad=False)
     assert g_none is None
     np.testing.assert_allclose(c_only.numpy(), c_dev.numpy(), rtol=1e-6)
+
+
+def _hostile_cases():
+    rng = np.random.default_rng(0)
+    cases = {}
+    for sigma in (20.0, 60.0):
+        cases[f"sigma{int(sigma)}"] = synth_problem(100 + int(sigma), 300, 4, 29, 40, 100, sigma=sigma)
+    T, B, V = 400, 3, 29
+    ll = np.array([150, 60, 0], np.int32)
+    al = np.array([T, T - 37, T], np.int32)
+    labels = rng.integers(1, V, int(ll.sum())).astype(np.int32)
+    acts = rng.standard_normal((T, B, V)).astype(np.float32)
+    acts[..., 0] += 30.0                                   # blank-collapsed model asked for long transcripts
+    cases["blank_saturated"] = (acts, labels, al, ll)
+    acts2 = rng.standard_normal((T, B, V)).astype(np.float32)
+    wrong = rng.integers(1, V, (T, B))
+    np.put_along_axis(acts2, wrong[..., None], 65.0, axis=2)  # confident and wrong on every frame
+    cases["confident_wrong"] = (acts2, labels, al, ll)
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_hostile_cases()))
+def test_out_of_range_utterances_fall_back_to_log_space(name):
+    """Inputs whose alpha/beta columns span more than the fp64 exponent range (cost of thousands of nats) cannot
+    be done in the linear domain; the engine must detect that and redo them in fp64 log space -- never a silent
+    +inf or a wrong gradient."""
+    from oracle import ctc_f64
+    acts, labels, al, ll = _hostile_cases()[name]
+    costs, grads, status = _engine(acts, labels, al, ll)
+    oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
+    assert np.isfinite(oc).all()
+    _assert_close(costs, grads, oc, og, name)
+    assert (status & 0x10).any(), "expected at least one utterance to take the log-space path"
+    assert not (status & 0x8).any()
+    # the host-buffer entry point takes the same detour
+    from aes_lac_2018_b200 import ctc_loss_host
+    c_h, g_h, st_h = ctc_loss_host(torch.tensor(acts).pin_memory(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), n_chunks=2)
+    _assert_close(c_h.numpy().astype(np.float64), g_h.numpy().astype(np.float64), oc, og, name + "/host")
