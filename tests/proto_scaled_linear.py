@@ -22,7 +22,7 @@ def _hiword_round(x):
     truncation error with a factor 1 + 2^-21 on the posterior scale), like the smem alpha column."""
     u = np.asarray(x, dtype=np.float64).view(np.uint64)
     u = u & np.uint64(0xFFFFFFFF00000000)
-    return u.view(np.float64) * (1.0 + 2.0 ** -21)
+    return u.view(np.float64) * (1.0 + 0.7213 * 2.0 ** -21)
 
 
 def _rescale(v, target):

@@ -86,7 +86,7 @@ def test_synthetic_vs_f64_oracle(name, mode):
     costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
     oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
     _assert_close(costs, grads, oc, og, name)
-    assert not (status & 0x8).any(), "range flag raised on a benign input"
+    assert not (status & 0x18).any(), "range flag / log-space detour on a benign input"
 
 
 def test_edge_cases_batch():
@@ -254,7 +254,7 @@ def test_full_size_properties_c4():
     al = torch.full((B,), T, dtype=torch.int32)
     labels = torch.randint(1, V, (int(ll.sum()),), generator=g, dtype=torch.int32)
     costs, grads, status = ctc_loss_raw(acts.cuda(), labels, al, ll, mode="throughput")
-    assert not status.any()
+    assert not status.any(), f"unexpected status bits {sorted(set(status.tolist()))} ({int((status != 0).sum())} utterances)"
     assert torch.isfinite(costs).all() and torch.isfinite(grads).all()
     assert grads.sum(-1).abs().max().item() < 5e-6                        # rows sum to zero
     # batch independence: utterance b alone gives bit-identical numbers

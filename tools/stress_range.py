@@ -19,10 +19,13 @@ def run(name, acts, labels, al, ll):
     c = costs.numpy().astype(np.float64); g = grads.cpu().numpy().astype(np.float64)
     fin = np.isfinite(oc)
     rel = np.abs(c[fin] - oc[fin]) / np.maximum(1, np.abs(oc[fin]))
-    print(name, "status", sorted(set(st.tolist())), "cost", oc[:3].round(1), "rel %.2e" % (rel.max() if rel.size else 0), "grad err %.2e" % np.abs(g - og).max())
+    err = np.abs(g - og).max(axis=(0, 2))
+    unfl = err[(st & 0x10) == 0]
+    print(name, "status", sorted(set(st.tolist())), "cost", oc[:3].round(1), "rel %.2e" % (rel.max() if rel.size else 0),
+          "grad err %.2e" % err.max(), "| worst UNFLAGGED %.2e" % (unfl.max() if unfl.size else 0), "flagged", int(((st & 0x10) != 0).sum()), "/", len(st))
 
-for sigma in (5, 10, 20, 40, 80):
-    acts, labels, al, ll = synth_problem(100 + sigma, 300, 4, 29, 40, 100, sigma=float(sigma))
+for sigma in (5, 10, 12, 14, 16, 18, 20, 22, 25, 30, 40, 80):
+    acts, labels, al, ll = synth_problem(100 + sigma, 300, 16, 29, 40, 100, sigma=float(sigma))
     run(f"sigma{sigma}", acts, labels, al, ll)
 # confident and wrong: every frame puts +25 on a symbol that is NOT in the transcript order
 rng = np.random.default_rng(0)
@@ -40,3 +43,9 @@ run("confident_wrong_65", acts2, labels, al, ll)
 # blank-saturated model asked for many labels
 acts3 = rng.standard_normal((T, B, V)).astype(np.float32); acts3[..., 0] += 30.0
 run("blank_saturated_30", acts3, labels, al, ll)
+
+for margin in (4, 6, 8, 10, 12, 15, 20):
+    acts3 = rng.standard_normal((T, 8, V)).astype(np.float32); acts3[..., 0] += float(margin)
+    ll8 = rng.integers(60, 201, 8).astype(np.int32); al8 = np.full(8, T, np.int32)
+    lab8 = rng.integers(1, V, int(ll8.sum())).astype(np.int32)
+    run(f"blank_margin_{margin}", acts3, lab8, al8, ll8)
