@@ -71,7 +71,7 @@ struct Plan {
 
 // forced_w: 0 = automatic ladder choice; otherwise use the latency ladder entry with that W where possible
 ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V, int B, int T_max,
-                      bool want_grad, int mode, Plan &plan)
+                      bool want_grad, int mode, Plan &plan, bool size_only = false)
 {
     if (!label_lengths || !input_lengths) return fail(CTC_STATUS_INVALID_VALUE, "null length array");
     if (V <= 0 || B <= 0 || T_max < 0) return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
@@ -107,18 +107,41 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     const Variant *ladder = ladder_table(mode == 2 ? LADDER_LATENCY : (mode == 3 ? LADDER_THROUGHPUT_K8 : LADDER_THROUGHPUT),
                                          vch, &nl);
 
-    // bucket utterances by variant, longest first inside a bucket (tail balance)
-    std::vector<std::pair<int, int>> order(B);       // (variant index, b)
+    // bucket utterances by variant (counting sort: big variants first), longest first inside a bucket when the
+    // lengths are ragged (tail balance).  O(B) unless T varies.
+    std::vector<int> cls(B);
+    std::vector<int> count(nl, 0);
+    int t_min = 0x7fffffff, t_max = 0;
     for (int b = 0; b < B; ++b) {
         const Variant *v = pick(ladder, nl, label_len[b]);
         if (!v) return fail(CTC_STATUS_UNKNOWN_ERROR, "no kernel variant for this label length");
-        order[b] = {(int)(v - ladder), b};
+        cls[b] = (int)(v - ladder);
+        ++count[cls[b]];
+        t_min = std::min(t_min, act_len[b]);
+        t_max = std::max(t_max, act_len[b]);
     }
-    std::stable_sort(order.begin(), order.end(), [&](const std::pair<int, int> &x, const std::pair<int, int> &y) {
-        if (x.first != y.first) return x.first > y.first;            // big variants first
-        return act_len[x.second] > act_len[y.second];
-    });
-    for (int i = 0; i < B; ++i) utt_ids[i] = order[i].second;
+    std::vector<int> start(nl + 1, 0);                   // launch order: descending variant index
+    for (int c = nl - 1, o2 = 0; c >= 0; --c) { start[c] = o2; o2 += count[c]; }
+    if (!size_only) {
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        for (int b = 0; b < B; ++b) utt_ids[fill[cls[b]]++] = b;
+        if (t_min != t_max) {
+            std::vector<unsigned long long> keys;
+            for (int c = 0; c < nl; ++c) {
+                if (count[c] < 2) continue;
+                keys.resize(count[c]);
+                int *seg = utt_ids + start[c];
+                for (int i = 0; i < count[c]; ++i)      // descending T, ascending index
+                    keys[i] = ((unsigned long long)(unsigned)(0x7fffffff - act_len[seg[i]]) << 32) | (unsigned)seg[i];
+                std::sort(keys.begin(), keys.end());
+                for (int i = 0; i < count[c]; ++i) seg[i] = (int)(keys[i] & 0xffffffffu);
+            }
+        }
+    }
+    struct Order { int first; };
+    std::vector<Order> order(B);                          // variant index per launch-ordered slot
+    for (int c = nl - 1; c >= 0; --c)
+        for (int i = 0; i < count[c]; ++i) order[start[c] + i].first = c;
 
     size_t o = 0;
     plan.off_meta = o;   o = align_up(o + sizeof(int) * 4 * (size_t)B, 256);
@@ -196,6 +219,21 @@ bool check(cudaError_t e, const char *what, ctcStatus_t code, ctcStatus_t &out)
     if (e == cudaSuccess) return true;
     out = fail(code, std::string(what) + ": " + cudaGetErrorString(e));
     return false;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (thread, device, kernel, size) instead of per launch
+bool ensure_smem_attr(const void *kernel, int smem, ctcStatus_t &st)
+{
+    struct Key { const void *k; int dev; int smem; };
+    thread_local std::vector<Key> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const Key &e : done)
+        if (e.k == kernel && e.dev == dev && e.smem >= smem) return true;
+    if (!check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+               "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return false;
+    done.push_back(Key{kernel, dev, smem});
+    return true;
 }
 
 constexpr unsigned kFlagForceLogspace = 0x80000000u;    // internal: skip the fused kernels, log-space for every utterance
@@ -305,8 +343,7 @@ ctcStatus_t run(const ctcB200Call &c)
                 n_aux_used = li;
             }
         }
-        if (!check(cudaFuncSetAttribute(l.v->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, l.smem),
-                   "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        if (!ensure_smem_attr((const void *)l.v->kernel, l.smem, st)) return st;
         l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);
         ++g_launches;
         ++li;
@@ -560,7 +597,7 @@ ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_l
     for (int mode = 1; mode <= 3; ++mode) {
         Plan p;
         ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
-                                   want_gradients != 0, mode, p);
+                                   want_gradients != 0, mode, p, /*size_only=*/true);
         if (st != CTC_STATUS_SUCCESS) return st;
         need = std::max(need, p.total);
     }

@@ -34,6 +34,20 @@ def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
     return x.detach().to(device="cpu", dtype=torch.int32).reshape(-1).contiguous()
 
 
+_dev_ws = {}
+
+
+def _grow_workspace(lib, key, label_lens_h, act_lens_h, V, B, T, want_grad, device):
+    need = ctypes.c_size_t(0)
+    st = lib.ctc_b200_workspace_size(label_lens_h.data_ptr(), act_lens_h.data_ptr(), V, B, T,
+                                     1 if want_grad else 0, ctypes.byref(need))
+    if st != _lib.CTC_STATUS_SUCCESS:
+        raise RuntimeError("ctc_b200_workspace_size: " + _lib.status_string(lib, st))
+    old = _dev_ws.pop(key, None)
+    del old                                                  # release before the larger allocation
+    return torch.empty(int(need.value * 1.25) + (1 << 20), dtype=torch.uint8, device=device)
+
+
 def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
                  grad_scale: float = 1.0, mode: str = "auto", debug: torch.Tensor | None = None,
                  serial_launches: bool = False, timing: dict | None = None):
@@ -62,12 +76,13 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         labels_h = torch.zeros(1, dtype=torch.int32)
 
     with torch.cuda.device(acts_d.device):
-        need = ctypes.c_size_t(0)
-        st = lib.ctc_b200_workspace_size(label_lens_h.data_ptr(), act_lens_h.data_ptr(), V, B, T,
-                                         1 if want_grad else 0, ctypes.byref(need))
-        if st != _lib.CTC_STATUS_SUCCESS:
-            raise RuntimeError("ctc_b200_workspace_size: " + _lib.status_string(lib, st))
-        workspace = torch.empty(need.value, dtype=torch.uint8, device=acts_d.device)
+        # The workspace is cached per device and only grows; its required size is recomputed (an O(B) host pass)
+        # only when the engine reports that the cached one is too small.
+        stream_ptr = torch.cuda.current_stream(acts_d.device).cuda_stream
+        key = (acts_d.device.index, stream_ptr)               # one workspace per (device, stream): calls on one stream serialise
+        workspace = _dev_ws.get(key)
+        if workspace is None:
+            workspace = _dev_ws[key] = _grow_workspace(lib, key, label_lens_h, act_lens_h, V, B, T, want_grad, acts_d.device)
         grads = torch.empty((T, B, V), dtype=torch.float32, device=acts_d.device) if want_grad else None
         costs = torch.empty(B, dtype=torch.float32)
         status = torch.empty(B, dtype=torch.int32)
@@ -86,8 +101,8 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         call.costs_device = None
         call.status_host = status.data_ptr()
         call.workspace = workspace.data_ptr()
-        call.workspace_bytes = need.value
-        call.stream = torch.cuda.current_stream(acts_d.device).cuda_stream
+        call.workspace_bytes = workspace.numel()
+        call.stream = stream_ptr
         call.debug_device = debug.data_ptr() if debug is not None else None
         kms = ctypes.c_float(0.0)
         call.kernel_ms_host = ctypes.cast(ctypes.pointer(kms), ctypes.c_void_p) if timing is not None else None
@@ -96,6 +111,10 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         if serial_launches:
             call.flags |= _lib.FLAG_SERIAL_LAUNCHES
         st = lib.ctc_b200_compute(ctypes.byref(call))
+        if st != _lib.CTC_STATUS_SUCCESS and b"workspace too small" in lib.ctc_b200_last_error():
+            workspace = _dev_ws[key] = _grow_workspace(lib, key, label_lens_h, act_lens_h, V, B, T, want_grad, acts_d.device)
+            call.workspace, call.workspace_bytes = workspace.data_ptr(), workspace.numel()
+            st = lib.ctc_b200_compute(ctypes.byref(call))
         if st != _lib.CTC_STATUS_SUCCESS:
             raise RuntimeError("ctc_b200_compute: " + _lib.status_string(lib, st))
         if timing is not None:
