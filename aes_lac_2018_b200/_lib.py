@@ -82,7 +82,7 @@ class CtcB200HostCall(ctypes.Structure):
 
 EXPORTS = ("get_warpctc_version", "ctcGetStatusString", "compute_ctc_loss", "get_workspace_size",
            "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info",
-           "ctc_b200_workspace_size_host", "ctc_b200_compute_host")
+           "ctc_b200_workspace_size_host", "ctc_b200_compute_host", "ctc_b200_greedy_decode")
 
 _lib = None
 
@@ -123,6 +123,10 @@ def load() -> ctypes.CDLL:
         ctypes.POINTER(ctypes.c_size_t)]
     lib.ctc_b200_compute_host.restype = ctypes.c_int
     lib.ctc_b200_compute_host.argtypes = [ctypes.POINTER(CtcB200HostCall)]
+    lib.ctc_b200_greedy_decode.restype = ctypes.c_int
+    lib.ctc_b200_greedy_decode.argtypes = [
+        ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     lib.ctc_b200_compute.restype = ctypes.c_int
     lib.ctc_b200_compute.argtypes = [ctypes.POINTER(CtcB200Call)]
     _lib = lib

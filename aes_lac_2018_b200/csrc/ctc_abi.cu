@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/ctc.h"
+#include "ctc_decode.cuh"
 #include "ctc_logspace.cuh"
 #include "ctc_variants.h"
 
@@ -629,6 +630,28 @@ ctcStatus_t ctc_b200_compute_host(const ctcB200HostCall *call)
 {
     if (!call) return fail(CTC_STATUS_INVALID_VALUE, "null call");
     return run_host(*call);
+}
+
+ctcStatus_t ctc_b200_greedy_decode(const float *probs, long long stride_b, long long stride_t, const int *sizes_device,
+                                   int minibatch, int max_time, int alphabet_size, int blank_label, int *tokens_device,
+                                   int *offsets_device, int *counts_device, CUstream stream)
+{
+    if (!probs || !tokens_device || !counts_device) return fail(CTC_STATUS_INVALID_VALUE, "null pointer argument");
+    if (minibatch <= 0 || max_time <= 0 || alphabet_size <= 0) return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
+    if (alphabet_size > 128) return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 128 is not supported by this build");
+    DecodeParams D;
+    D.probs = probs; D.stride_b = stride_b; D.stride_t = stride_t; D.sizes = sizes_device;
+    D.tokens = tokens_device; D.offsets = offsets_device; D.counts = counts_device;
+    D.B = minibatch; D.T = max_time; D.V = alphabet_size; D.blank = blank_label;
+    const int smem = 32 * (alphabet_size | 1) * (int)sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (alphabet_size <= 32) ctc_greedy_decode_kernel<1><<<minibatch, 32, smem, s>>>(D);
+    else if (alphabet_size <= 64) ctc_greedy_decode_kernel<2><<<minibatch, 32, smem, s>>>(D);
+    else ctc_greedy_decode_kernel<4><<<minibatch, 32, smem, s>>>(D);
+    ++g_launches;
+    ctcStatus_t st = CTC_STATUS_SUCCESS;
+    if (!check(cudaGetLastError(), "decode launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    return CTC_STATUS_SUCCESS;
 }
 
 ctcStatus_t get_workspace_size(const int *const label_lengths, const int *const input_lengths, int alphabet_size,

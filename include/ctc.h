@@ -194,6 +194,22 @@ ctcStatus_t ctc_b200_workspace_size_host(const int *label_lengths, const int *in
 
 ctcStatus_t ctc_b200_compute_host(const ctcB200HostCall *call);
 
+/*
+ * Greedy (best-path) decode of B x T x V activations or probabilities: per utterance, argmax over the alphabet
+ * for each frame t < sizes[b], collapse repeats, drop blanks.  Replaces GreedyDecoder.decode of the reference
+ * (/root/reference/codes/decoder.py:143-160: torch.max + a Python loop with one .item() per frame).
+ * Everything is DEVICE memory; the call only enqueues one kernel on `stream`.
+ *   probs            element (b, t, k) at b*stride_b + t*stride_t + k   (elements)
+ *   sizes_device     [minibatch] valid frames, or NULL for max_time
+ *   tokens_device    [minibatch][max_time]: the first counts[b] entries of row b are the decoded symbols
+ *   offsets_device   [minibatch][max_time] frame index of each decoded symbol, or NULL
+ *   counts_device    [minibatch]
+ */
+ctcStatus_t ctc_b200_greedy_decode(const float *probs, long long stride_b, long long stride_t,
+                                   const int *sizes_device, int minibatch, int max_time, int alphabet_size,
+                                   int blank_label, int *tokens_device, int *offsets_device, int *counts_device,
+                                   CUstream stream);
+
 /* Human-readable description of the last failure on the calling thread ("" if none). */
 const char *ctc_b200_last_error(void);
 
