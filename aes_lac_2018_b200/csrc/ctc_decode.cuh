@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(32) ctc_greedy_decode_kernel(const DecodeParam
     extern __shared__ float tile[];                       // [32][RS]
     constexpr int VMAX = 32 * VCH;
     const int lane = threadIdx.x, b = blockIdx.x;
-    const int V = P.V, RS = V | 1;
+    const int V = P.V, RS = V | 1;                        // odd row stride => conflict-free column walks
     const int size = P.sizes ? min(max(P.sizes[b], 0), P.T) : P.T;
     const float *base = P.probs + (long long)b * P.stride_b;
     int *tok = P.tokens + (long long)b * P.T;
@@ -46,13 +46,23 @@ __global__ void __launch_bounds__(32) ctc_greedy_decode_kernel(const DecodeParam
     float st[VMAX];
     auto issue = [&](int t0) {
         const float *src = base + (long long)t0 * V + lane;
-        const int n_el = min(32, size - t0) * V;
+        if (t0 + 32 <= size) {                            // full tile: no per-element bound
 #pragma unroll
-        for (int j = 0; j < VMAX; ++j)
-            st[j] = (j < V && lane + 32 * j < n_el) ? __ldg(src + 32 * j) : 0.f;
+            for (int j = 0; j < VMAX; ++j)
+                if (j < V) st[j] = __ldg(src + 32 * j);
+        } else {
+            const int n_el = (size - t0) * V;
+#pragma unroll
+            for (int j = 0; j < VMAX; ++j)
+                st[j] = (j < V && lane + 32 * j < n_el) ? __ldg(src + 32 * j) : 0.f;
+        }
     };
     auto stash = [&](int t0) {
-        if (dense) {
+        if (dense && (V & 1)) {                           // RS == V: the tile is stored exactly as it lies in HBM
+#pragma unroll
+            for (int j = 0; j < VMAX; ++j)
+                if (j < V) tile[lane + 32 * j] = st[j];
+        } else if (dense) {
             int row = lane / V, col = lane % V;
 #pragma unroll
             for (int j = 0; j < VMAX; ++j) {
@@ -75,12 +85,29 @@ __global__ void __launch_bounds__(32) ctc_greedy_decode_kernel(const DecodeParam
         if (dense && t0 + 32 < size) issue(t0 + 32);
         const int t = t0 + lane;
         int best = 0;
-        if (t < size) {
+        {
+            // first maximum wins.  The common case runs a 3-instruction compare/select per symbol; rows that
+            // contain a NaN (torch.max treats NaN as maximal, first NaN wins) are redone on a slow path.
             const float *row = tile + lane * RS;
             float bv = row[0];
-            for (int k = 1; k < V; ++k) {                 // first maximum wins; NaN counts as maximal (torch.max)
-                const float v = row[k];
-                if (v > bv || (v != v && bv == bv)) { bv = v; best = k; }
+            bool has_nan = (bv != bv);
+#pragma unroll
+            for (int k = 1; k < VMAX; ++k) {
+                if (k < V) {
+                    const float v = row[k];
+                    has_nan |= (v != v);
+                    const bool gt = v > bv;
+                    bv = gt ? v : bv;
+                    best = gt ? k : best;
+                }
+            }
+            if (has_nan) {
+                best = 0;
+                bv = row[0];
+                for (int k = 1; k < V; ++k) {
+                    const float v = row[k];
+                    if (v > bv || (v != v && bv == bv)) { bv = v; best = k; }
+                }
             }
         }
         int prev = __shfl_up_sync(0xffffffffu, best, 1);
