@@ -65,7 +65,7 @@ struct FusedParams {
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
 struct SmemLayout {
     int off_ptab, off_acol, off_bpart, off_btot, off_xch, off_zfin, off_raw, off_rinv, off_ea,
-        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, off_dbg, off_pstg, total;
+        off_lab, off_pos, off_cnt, off_off, off_misc, off_scr, off_cks, off_dbg, off_pstg, off_slot, total;
 };
 
 // bytes of one p~ image: the [VP+1][K+1] table of fp64 HIGH WORDS followed by the K fp32 reciprocal row sums,
@@ -99,6 +99,7 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_ea = o;    o += (nC + 1) * 4;
     l.off_lab = o;   o += LP * 4;
     l.off_pos = o;   o += LP * 4;
+    l.off_slot = o;  o += LP * 4;                           // product slot of every label position
     l.off_cnt = o;   o += (V + 1) * 4;
     l.off_off = o;   o += (V + 1) * 4;
     l.off_misc = o;  o += 8 * 4;
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     float *rinv = (float *)(smem + lay.off_rinv);           // [K] 1/rowsum (buffer 0; re-pointed per backward chunk)
     int *ea_s = (int *)(smem + lay.off_ea);                 // [nC] alpha exponent per chunk
     int *lab_s = (int *)(smem + lay.off_lab);               // [LP]
-    int *pos_s = (int *)(smem + lay.off_pos);               // [LP] acol element offsets grouped by symbol
+    int *pos_s = (int *)(smem + lay.off_pos);               // [LP] product slots grouped by symbol (list mode)
+    int *slot_s = (int *)(smem + lay.off_slot);             // [LP] product slot of label j
     int *cnt_s = (int *)(smem + lay.off_cnt);               // [V+1]
     int *off_s = (int *)(smem + lay.off_off);               // [V+1]
     int *misc = (int *)(smem + lay.off_misc);               // [0] repeats, [1] bad label
@@ -323,7 +325,15 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     }
     int pboff = lay.off_ptab + blank * (KP * 4);
 
-    // ---- per-symbol position lists (deterministic, ascending); entries are acol element offsets ----
+    // ---- where the alpha*beta product of each label goes, and how symbol k finds its labels -------------------
+    // Segment mode (W == 1): the products of one timestep are stored grouped by symbol in the (already consumed)
+    // alpha row of that timestep, symbol k owning the slots [off[k], off[k] + cnt[k]).  The segment starts are
+    // padded so that off[k] mod 32 is distinct for the symbols handled by one pass of the warp: at iteration q
+    // lane k then reads slot off[k] + q and all 32 lanes hit different banks -- the gather is conflict-free
+    // (it was the largest shared-memory consumer: 33 of ~110 wavefronts per utterance-timestep).
+    // List mode (W > 1, or the padded segments do not fit): products stay at their own state's position and
+    // symbol k walks a list of positions (ascending => deterministic either way).
+    bool seg_mode = false;
     if (want_grad) {
         for (int k = tid; k <= V; k += NT) {
             int c = 0;
@@ -331,21 +341,51 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             cnt_s[k] = c;
         }
         __syncthreads();
-        for (int k = tid; k <= V; k += NT) {
-            int o = 0;
-            for (int q = 0; q < k; ++q) o += cnt_s[q];
-            off_s[k] = o;
+        if (tid == 0) {
+            int ok = (W == 1);
+            if (ok) {
+                unsigned used = 0u;
+                int cur = 0;
+                for (int k = 0; k < V; ++k) {
+                    if ((k & 31) == 0) used = 0u;           // residues only need to differ within one 32-symbol pass
+                    int o = cur;
+                    if (cnt_s[k]) {
+                        while ((used >> (o & 31)) & 1u) ++o;
+                        used |= 1u << (o & 31);
+                        cur = o + cnt_s[k];
+                    }
+                    off_s[k] = o;
+                }
+                off_s[V] = cur;
+                ok = (cur <= SP);
+            }
+            if (!ok) {
+                int o = 0;
+                for (int k = 0; k <= V; ++k) { off_s[k] = o; o += (k < V) ? cnt_s[k] : 0; }
+            }
+            misc[2] = ok;
         }
         __syncthreads();
+        seg_mode = (misc[2] != 0);
         for (int k = tid; k < V; k += NT) {
             int q = off_s[k];
             if (cnt_s[k])
                 for (int j = 0; j < L; ++j)
                     if (lab_s[j] == k) {
                         const int s = 2 * j + 1;
-                        pos_s[q++] = (s % NS) * NT + (s / NS);      // [i][tid] offset inside one acol column
+                        const int own = (s % NS) * NT + (s / NS);   // [i][tid] offset of the label's own state
+                        slot_s[j] = seg_mode ? q : own;
+                        if (!seg_mode) pos_s[q] = own;
+                        ++q;
                     }
         }
+        __syncthreads();
+    }
+    int sl[NL];                                             // product slot of this thread's labels
+#pragma unroll
+    for (int jj = 0; jj < NL; ++jj) {
+        const int j = j0 + jj;
+        sl[jj] = (want_grad && j < L) ? slot_s[j] : -1;      // no label here: nothing to store
     }
     if (tid < 2 * W * 2) xch[tid] = 0.0;
     if (tid < 2) zfin[tid] = 0.0;
@@ -632,20 +672,24 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                 }
                 const double pb = __hiloint2double(*(const int *)(smem + pboff + tt * 4), 0);
                 double bsum = 0.0;
+                // all alpha values of this timestep are read BEFORE any product is written: in segment mode a
+                // product lands in a slot that held another lane's alpha of the same timestep
+                double av[NS];
+#pragma unroll
+                for (int i = 0; i < NS; ++i) av[i] = __hiloint2double((int)acol[(tt * NS + i) * NT + tid], 0);
+                if (W == 1) __syncwarp();
 #pragma unroll
                 for (int i = 0; i < NS; ++i) {
-                    unsigned *ap = acol + (tt * NS + i) * NT + tid;
-                    const double av = __hiloint2double((int)*ap, 0);
                     if (i & 1) {
                         const int jj = i >> 1;
                         const double pl = __hiloint2double(*(const int *)(smem + poff[jj] + tt * 4), 0);
                         const double n1 = (i + 1 < NS) ? bt[i + 1] : dn0;
                         const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
                         bt[i] = fma(msk[jj + 1], n2, bt[i] + n1) * pl;
-                        *ap = __float_as_uint((float)(av * bt[i] * sc));
+                        if (sl[jj] >= 0) acol[tt * SP + sl[jj]] = __float_as_uint((float)(av[i] * bt[i] * sc));
                     } else {
                         bt[i] = (bt[i] + bt[i + 1]) * pb;
-                        bsum = fma(av, bt[i], bsum);
+                        bsum = fma(av[i], bt[i], bsum);
                     }
                 }
                 bpart[tt * NT + tid] = (float)(bsum * sc);
@@ -686,9 +730,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             } else {
 #pragma unroll
                 for (int u = 0; u < TG; ++u) acc[u] = 0.f;
-                const int q1 = off_s[k + 1];
-                for (int q = off_s[k]; q < q1; ++q) {
-                    const float *gp = (const float *)acol + tt0 * (NS * NT) + pos_s[q];
+                const int q0 = off_s[k], q1 = q0 + cnt_s[k];
+                for (int q = q0; q < q1; ++q) {
+                    const float *gp = (const float *)acol + tt0 * (NS * NT) + (seg_mode ? q : pos_s[q]);
 #pragma unroll
                     for (int u = 0; u < TG; ++u) acc[u] += gp[u * (NS * NT)];
                 }
