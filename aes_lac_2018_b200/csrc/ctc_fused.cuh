@@ -89,13 +89,13 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_pstg = o;  o += pimg_bytes(K, V);                 // image buffer 1 (the backward sweep alternates)
     o = (o + 7) & ~7;
     l.off_acol = o;  o += K * SP * 4;                       // [K][NS][NT] 32-bit: alpha high words, then float products
-    l.off_bpart = o; o += K * NT * 4;                       // [K][NT] floats: per-thread blank posterior mass
+    l.off_bpart = o; o += K * (NT + 32) * 4;                // [K][NT + RB] floats: per-thread blank posterior mass
     l.off_btot = o;  o += ((K + 1) & ~1) * 4;               // [K] floats
     l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT] doubles
     l.off_dbg = o;   o += 16 * 8;                           // phase cycle counters (profiling aid)
     l.off_xch = o;   o += 2 * W * 2 * 8;
     l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
-    l.off_raw = o;   o += K * (VP + 1) * 4;                 // [K][VP+1] staged raw activations, pad columns = -inf
+    l.off_raw = o;   o += K * (VP + 32) * 4;                // [K][VP + G] staged raw activations, pad columns = -inf
     l.off_ea = o;    o += (nC + 1) * 4;
     l.off_lab = o;   o += LP * 4;
     l.off_pos = o;   o += LP * 4;
@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int NL = NS / 2;                 // labels per thread
     constexpr int VP_ = 32 * VCH;
     constexpr int KP = K + 1;                  // ptab row stride (32-bit words; odd => symbols map to distinct banks)
-    constexpr int RS = VP_ + 1;                // raw row stride (odd => rows map to distinct banks)
+    constexpr int GG = (32 * W / K) < 32 ? (32 * W / K) : 32;
+    constexpr int RS = VP_ + (GG < 32 ? GG : 1);   // raw row stride == lanes-per-row (mod 32): the (row, lane-in-row)
+                                               // pairs of one softmax load land in distinct banks
+    constexpr int BS = 32 * W + (GG < 32 ? GG : 1);  // bpart row stride, same argument for the blank reduction
     constexpr int G = (NT / K) < 32 ? (NT / K) : 32;   // lanes per softmax row
     constexpr int RP = NT / G;                 // rows per softmax pass
     constexpr int NPASS = (K + RP - 1) / RP;
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     }
     for (int i = tid; i < K * RS; i += NT) raw[i] = -INFINITY;       // pad columns stay -inf (p~ = 0)
     for (int i = tid; i < K * SP; i += NT) acol[i] = 0u;              // (frames of a partial last chunk are read
-    for (int i = tid; i < K * NT; i += NT) bpart[i] = 0.f;            //  -- and masked -- before they are written)
+    for (int i = tid; i < K * BS; i += NT) bpart[i] = 0.f;            //  -- and masked -- before they are written)
     __syncthreads();
 
     const int nC = (T + K - 1) / K;
@@ -692,7 +695,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
                         bsum = fma(av[i], bt[i], bsum);
                     }
                 }
-                bpart[tt * NT + tid] = (float)(bsum * sc);
+                bpart[tt * BS + tid] = (float)(bsum * sc);
                 if (W > 1) {
                     if (lane == 0) {
                         xch[((bpar ^ 1) * W + warp) * 2] = bt[0];
@@ -711,7 +714,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             const int tt = tid / RB, q = tid % RB;
             float s = 0.f;
             if (tt < K)
-                for (int x = q; x < NT; x += RB) s += bpart[tt * NT + x];
+                for (int x = q; x < NT; x += RB) s += bpart[tt * BS + x];
 #pragma unroll
             for (int o = RB / 2; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (tt < K && q == 0) btot[tt] = s;
