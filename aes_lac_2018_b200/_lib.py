@@ -13,6 +13,7 @@ CTC_GPU = 1
 FLAG_NO_SYNC = 0x1
 FLAG_SERIAL_LAUNCHES = 0x2
 FLAG_NO_FALLBACK = 0x4
+FLAG_NO_BIDIR = 0x8
 FLAG_MODE_THROUGHPUT = 1 << 8
 FLAG_MODE_LATENCY = 2 << 8
 FLAG_MODE_THROUGHPUT_K8 = 3 << 8

@@ -17,7 +17,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libctc_b200.so")
 N_GROUPS = 6
-HEADERS = ["ctc_fused.cuh", "ctc_logspace.cuh", "ctc_decode.cuh", "ctc_variants.h", "ctc_variants.cu", "ctc_abi.cu", os.path.join(ROOT, "include", "ctc.h")]
+HEADERS = ["ctc_fused.cuh", "ctc_logspace.cuh", "ctc_decode.cuh", "ctc_combine.cuh", "ctc_variants.h", "ctc_variants.cu", "ctc_abi.cu", os.path.join(ROOT, "include", "ctc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

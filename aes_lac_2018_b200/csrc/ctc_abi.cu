@@ -35,6 +35,7 @@ ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
 // SP = 32*NS*W padded states; an utterance with L labels fits when SP >= 2L + 2.
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
+constexpr int kBidirMaxB = 128;              // bidirectional (two sweeps + combine) path for batches up to this size
 
 const Variant *ladder_table(int ladder, int vch, int *n)
 {
@@ -63,7 +64,9 @@ struct Plan {
     int B = 0, T_max = 0, V = 0;
     bool latency = false;
     std::vector<int> meta;                   // [label_off B | label_len B | act_len B | utt_ids B]
-    struct Launch { const Variant *v; int first, count; size_t ckpt_off; long long ckpt_stride; int smem; };
+    struct Launch { const Variant *v; int first, count; size_t ckpt_off; long long ckpt_stride; int smem;
+                    size_t col_off, exp_off, z_off; int exp_stride; };   // bidirectional path (column spill) offsets
+    bool bidir = false;
     std::vector<Launch> launches;
     long long total_labels = 0;
     size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_ckpt = 0, total = 0, ckpt_bytes = 0;
@@ -150,7 +153,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     plan.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
     plan.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
     plan.off_ckpt = o;
-    size_t ck = 0;
+    size_t ck = 0, bd = 0;
+    plan.bidir = plan.latency && want_grad && B <= kBidirMaxB;
     for (int i = 0; i < B;) {
         int j = i;
         while (j < B && order[j].first == order[i].first) ++j;
@@ -162,13 +166,20 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
         l.ckpt_off = ck;
         ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.count;
+        // bidirectional path: 2 slots (forward, reversed) of T_max columns of SP high words, exponents, Z
+        l.exp_stride = nC + 2;
+        l.col_off = bd;  bd = align_up(bd + sizeof(unsigned) * 2 * (size_t)l.count * (size_t)T_max * v->sp(), 256);
+        l.exp_off = bd;  bd = align_up(bd + sizeof(int) * 2 * (size_t)l.count * l.exp_stride, 256);
+        l.z_off = bd;    bd = align_up(bd + sizeof(double) * 2 * (size_t)l.count * 4, 256);
         l.smem = make_layout(v->NS, v->W, v->K, V, T_max).total;
         if (l.smem > kMaxSmem)
             return fail(CTC_STATUS_UNKNOWN_ERROR,
                         "alphabet_size / max_time too large for the shared-memory layout of this kernel");
+        if (plan.bidir && (!v->combine || combine_smem_bytes(v->sp(), V) > kMaxSmem)) plan.bidir = false;
         plan.launches.push_back(l);
         i = j;
     }
+    if (plan.bidir) ck = std::max(ck, bd);
     // the checkpoint area doubles as the alpha store of the log-space fallback: keep room for one utterance
     plan.fallback_S = 2 * max_L + 1;
     ck = std::max(ck, sizeof(double) * (size_t)std::max(T_max, 1) * (size_t)plan.fallback_S);
@@ -329,6 +340,9 @@ ctcStatus_t run(const ctcB200Call &c)
     AuxStreams *aux = (plan.launches.size() > 1 && !serial) ? aux_streams() : nullptr;
     if (aux && !check(cudaEventRecord(aux->fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     const bool force_log = (c.flags & kFlagForceLogspace) != 0;
+    const bool bidir = plan.bidir && want_grad && !force_log && !(c.flags & CTC_B200_FLAG_NO_BIDIR);
+    P.sweep_only = 0; P.n_fwd = 0; P.col = nullptr; P.col_stride = 0; P.col_exp = nullptr; P.col_exp_stride = 0;
+    P.col_z = nullptr;
     int n_aux_used = 0, li = 0;
     for (const Plan::Launch &l : plan.launches) {
         if (force_log) break;
@@ -345,7 +359,32 @@ ctcStatus_t run(const ctcB200Call &c)
             }
         }
         if (!ensure_smem_attr((const void *)l.v->kernel, l.smem, st)) return st;
-        l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);
+        if (bidir) {
+            // small batch: the T-serial chain is the bound.  Two concurrent forward sweeps per utterance (the problem
+            // and its time/label reversal) spill their columns; ctc_combine_kernel forms the gradients in parallel.
+            char *area = ws + plan.off_ckpt;
+            P.sweep_only = 1; P.n_fwd = l.count;
+            P.col = (unsigned *)(area + l.col_off); P.col_stride = (long long)c.max_time * l.v->sp();
+            P.col_exp = (int *)(area + l.exp_off); P.col_exp_stride = l.exp_stride;
+            P.col_z = (double *)(area + l.z_off);
+            l.v->kernel<<<2 * l.count, 32 * l.v->W, l.smem, ls>>>(P);
+            ++g_launches;
+            if (!check(cudaGetLastError(), "kernel launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+            CombineParams C;
+            C.acts = P.acts; C.act_stride_t = P.act_stride_t; C.act_stride_b = P.act_stride_b; C.grads = P.grads;
+            C.labels = P.labels; C.label_off = P.label_off; C.label_len = P.label_len; C.act_len = P.act_len;
+            C.utt_ids = P.utt_ids; C.status = P.status;
+            C.col = P.col; C.col_stride = P.col_stride; C.col_exp = P.col_exp; C.col_exp_stride = P.col_exp_stride;
+            C.col_z = P.col_z; C.n = l.count;
+            C.V = V; C.T_max = c.max_time; C.B = B; C.blank = c.blank_label; C.grad_scale = c.grad_scale;
+            C.frames_per_cta = 8;
+            const int csm = combine_smem_bytes(l.v->sp(), V);
+            if (!ensure_smem_attr((const void *)l.v->combine, csm, st)) return st;
+            dim3 grid((c.max_time + C.frames_per_cta - 1) / C.frames_per_cta, l.count);
+            l.v->combine<<<grid, kCombineThreads, csm, ls>>>(C);
+        } else {
+            l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);
+        }
         ++g_launches;
         ++li;
         if (!check(cudaGetLastError(), "kernel launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;

@@ -60,6 +60,14 @@ struct FusedParams {
     int V, T_max, B, blank;
     float grad_scale;
     long long *debug;                 // optional [B][16]: fwd cycles, total cycles, total ns, smid, 12 phase counters
+    // --- bidirectional mode (small batches, see ctc_combine.cuh): forward sweep only, every column spilled ---
+    int sweep_only;                   // 1: no backward sweep; CTAs >= n_fwd run the time- and label-REVERSED problem
+    int n_fwd;                        // number of forward CTAs (= utterances of this launch)
+    unsigned *col;                    // [gridDim.x] slots of [T_max][NS][NT] alpha high words
+    long long col_stride;             // words per slot
+    int *col_exp;                     // [gridDim.x][col_exp_stride] alpha exponent of every chunk
+    int col_exp_stride;
+    double *col_z;                    // [gridDim.x][4]: Z^, Ea_fin, log Z (natural), unused
 };
 
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
@@ -262,7 +270,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     unsigned *scratch = (unsigned *)(smem + lay.off_scr);   // [W] cross-warp max
     double *cks = (double *)(smem + lay.off_cks);           // [NS][NT] checkpoint column staged by cp.async
 
-    const int b = P.utt_ids[blockIdx.x];
+    const bool rev = P.sweep_only && (int)blockIdx.x >= P.n_fwd;     // reversed twin of utterance blockIdx.x - n_fwd
+    const int b = P.utt_ids[rev ? blockIdx.x - P.n_fwd : blockIdx.x];
     long long dbg_c0 = 0, dbg_n0 = 0, dbg_c1 = 0;
     if (P.debug && tid == 0) {
         dbg_c0 = clock64();
@@ -283,7 +292,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     const float *acts_b = P.acts + (long long)b * P.act_stride_b;
     float *grads_b = P.grads ? P.grads + (long long)b * V : nullptr;
     const long long gst = (long long)P.B * V;               // gradient row stride (dense)
-    const bool want_grad = (P.grads != nullptr);
+    const bool sweep_only = (P.sweep_only != 0);
+    const bool want_grad = (P.grads != nullptr) && !sweep_only;      // (sweep-only: gradients come from ctc_combine_kernel)
 
     // ---- labels -> shared, repeats, validity ----
     if (tid < 8) misc[tid] = 0;
@@ -293,9 +303,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         for (int j = tid; j < LP; j += NT) {
             int v = -1;
             if (j < L) {
-                v = lab_g[j];
+                v = lab_g[rev ? L - 1 - j : j];
                 if (v < 0 || v >= V || v == blank) { bad = 1; v = -1; }
-                else if (j > 0 && lab_g[j - 1] == v) rep++;
+                else if (j > 0 && lab_g[rev ? L - j : j - 1] == v) rep++;
             }
             lab_s[j] = v;
         }
@@ -307,8 +317,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     if (misc[1]) ustat |= UTT_BAD_LABEL;
     if (T <= 0 || L + misc[0] > T) ustat |= UTT_INFEASIBLE;
     if (ustat) {                                            // cost 0, gradient 0 (warp-ctc CPU convention)
-        if (tid == 0) { P.costs[b] = 0.f; P.status[b] = ustat; }
-        if (want_grad)
+        if (tid == 0 && !rev) { P.costs[b] = 0.f; P.status[b] = ustat; }
+        if (P.grads != nullptr && !rev)
             for (int t = warp; t < P.T_max; t += W)
                 for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
         return;
@@ -413,8 +423,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     float xr[RPW][VCH];
     auto issue_loads = [&](int c) {
         const int t0 = c * K, n = min(K, T - t0);
-        const float *src = acts_b + (long long)(t0 + warp) * P.act_stride_t + lane;
-        const long long rstep = (long long)W * P.act_stride_t;
+        const float *src = acts_b + (long long)(rev ? T - 1 - (t0 + warp) : t0 + warp) * P.act_stride_t + lane;
+        const long long rstep = (rev ? -1LL : 1LL) * W * P.act_stride_t;
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
             const int r = warp + rr * W;
@@ -541,6 +551,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             for (int i = 0; i < NS; ++i) ck[((long long)c * NS + i) * NT + tid] = a[i];
             if (tid == 0) ea_s[c] = Ea;
         }
+        if (sweep_only && tid == 0) P.col_exp[(long long)blockIdx.x * P.col_exp_stride + c] = Ea;
         phase(1);                                           // 1: fwd rescale + checkpoint store
         stash_rows();                                       // (previous chunk's readers of raw/ptab are past their sync)
         if (c + 1 < nC) issue_loads(c + 1);
@@ -557,6 +568,11 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         for (int tt = 0; tt < K; ++tt) {
             if (tt >= n) break;
             alpha_step(a, tt, par);
+            if (sweep_only) {                               // bidirectional mode: every column goes to HBM/L2
+                unsigned *cp = P.col + (long long)blockIdx.x * P.col_stride + (long long)(c * K + tt) * SP + tid;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) cp[i * NT] = (unsigned)__double2hiint(a[i]);
+            }
         }
         phase(5);                                           // 5: fwd alpha steps
     }
@@ -587,10 +603,18 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     if (!(zhat == zhat) || zhat == INFINITY) ustat |= UTT_RANGE;
     else if (!z_ok) ustat |= UTT_INF_COST;
     if (tid == 0) {
-        float cost;
-        if (z_ok) cost = (float)(-(log(zhat) + (double)Ea_fin * 0.6931471805599453 - logsum));
-        else cost = INFINITY;
-        P.costs[b] = cost;
+        const double logz = z_ok ? (log(zhat) + (double)Ea_fin * 0.6931471805599453 - logsum) : -INFINITY;
+        if (!rev) P.costs[b] = z_ok ? (float)(-logz) : INFINITY;
+        if (sweep_only) {
+            double *z = P.col_z + (long long)blockIdx.x * 4;
+            z[0] = zhat; z[1] = (double)Ea_fin; z[2] = logz; z[3] = 0.0;
+        }
+    }
+    if (sweep_only) {
+        if (tid == 0 && !rev) P.status[b] = ustat;
+        if (P.grads != nullptr && !rev)                      // padded frames get zero gradient
+            for (int t = T + warp; t < P.T_max; t += W)
+                for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
     }
     if (P.debug && tid == 0) dbg_c1 = clock64();
     auto dbg_out = [&]() {
@@ -607,7 +631,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         }
     };
     if (!want_grad) {
-        if (tid == 0) P.status[b] = ustat;
+        if (tid == 0 && !sweep_only) P.status[b] = ustat;
         dbg_out();
         return;
     }

@@ -9,7 +9,11 @@ namespace ctcb200 {
 
 #define CTC_LADDER (CTC_GROUP / 2)
 #define CTC_VCH (CTC_GROUP % 2 + 1)
-#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>}
+#if CTC_GROUP / 2 == 2
+#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, ctc_combine_kernel<NS, W, K>}
+#else
+#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, nullptr}
+#endif
 
 static const Variant kTable[] = {
 #if CTC_LADDER == 0

@@ -2,6 +2,7 @@
 // Each translation unit ctc_variants.cu -DCTC_GROUP=g contributes one group; the groups are compiled in
 // parallel by aes_lac_2018_b200/build.py and linked into libctc_b200.so.
 #pragma once
+#include "ctc_combine.cuh"
 #include "ctc_fused.cuh"
 
 namespace ctcb200 {
@@ -9,6 +10,7 @@ namespace ctcb200 {
 struct Variant {
     int NS, W, K, VCH;
     void (*kernel)(const FusedParams);
+    void (*combine)(const CombineParams);      // latency ladder only: second half of the bidirectional path
     int max_label() const { return (32 * NS * W) / 2 - 1; }   // SP = 32*NS*W states must hold 2L+2
     int sp() const { return 32 * NS * W; }
 };

@@ -116,6 +116,7 @@ ctcStatus_t get_workspace_size(const int *const label_lengths,
 
 #define CTC_B200_FLAG_NO_SYNC 0x1u       /* do not synchronise; costs_host/status_host must be NULL */
 #define CTC_B200_FLAG_SERIAL_LAUNCHES 0x2u /* keep every kernel on `stream` (no internal fork/join streams) */
+#define CTC_B200_FLAG_NO_BIDIR 0x8u        /* small batches: keep the three-sweep fused kernel instead of the bidirectional path */
 #define CTC_B200_FLAG_NO_FALLBACK 0x4u     /* report out-of-range utterances instead of re-running them in log space */
 /* bits 8..9: variant ladder override (0 auto, 1 throughput, 2 latency, 3 throughput with 8-step chunks) */
 

@@ -21,10 +21,13 @@ TORCH_CASES = load_torch_f64_cases()
 def _engine(acts, labels, act_lens, label_lens, blank=0, mode="auto", want_grad=True):
     from aes_lac_2018_b200 import ctc_loss_raw
     a = torch.as_tensor(np.asarray(acts, dtype=np.float32)).cuda()
+    # "latency" = latency ladder with the bidirectional path for small batches; "latency3" = same ladder, three-sweep kernel
+    bidir = mode != "latency3"
     costs, grads, status = ctc_loss_raw(a, torch.as_tensor(np.asarray(labels, dtype=np.int32)),
                                         torch.as_tensor(np.asarray(act_lens, dtype=np.int32)),
                                         torch.as_tensor(np.asarray(label_lens, dtype=np.int32)),
-                                        blank=blank, want_grad=want_grad, mode=mode)
+                                        blank=blank, want_grad=want_grad, mode="latency" if mode == "latency3" else mode,
+                                        bidirectional=bidir)
     return costs.numpy().astype(np.float64), (grads.cpu().numpy().astype(np.float64) if want_grad else None), status.numpy()
 
 
@@ -39,7 +42,7 @@ def _assert_close(costs, grads, ref_costs, ref_grads, tag=""):
                                       f"per-utt max {d.max(axis=(0, 2))}")
 
 
-@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency"])
+@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency", "latency3"])
 @pytest.mark.parametrize("case", KNOWN, ids=[c["name"] for c in KNOWN])
 def test_known_answers(case, mode):
     from oracle import ctc_f64
@@ -57,7 +60,7 @@ def test_known_answers(case, mode):
     _assert_close(costs, grads, oc, og, case["name"])
 
 
-@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency"])
+@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency", "latency3"])
 @pytest.mark.parametrize("name", sorted(TORCH_CASES))
 def test_golden_torch_f64(name, mode):
     c = TORCH_CASES[name]
@@ -78,7 +81,7 @@ SYNTH = {
 }
 
 
-@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency"])
+@pytest.mark.parametrize("mode", ["throughput", "throughput8", "latency", "latency3"])
 @pytest.mark.parametrize("name", sorted(SYNTH))
 def test_synthetic_vs_f64_oracle(name, mode):
     from oracle import ctc_f64
@@ -99,7 +102,7 @@ def test_edge_cases_batch():
     al = np.array([24, 10, 11, 12, 8, 1, 1, 20], np.int32)
     labels = np.concatenate([np.full(18, 3), rng.integers(1, V, 9), [4], rng.integers(1, V, 5)]).astype(np.int32)
     acts = rng.standard_normal((T, len(ll), V)).astype(np.float32)
-    for mode in ("throughput", "throughput8", "latency"):
+    for mode in ("throughput", "throughput8", "latency", "latency3"):
         costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
         oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
         _assert_close(costs, grads, oc, og, "edge/" + mode)

@@ -84,7 +84,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = []
     cfgs = [
-        ("c1", 4, 200, 29, 10, 50), ("c2", 32, 750, 29, 50, 200), ("b256", 256, 750, 29, 50, 200),
+        ("c1", 4, 200, 29, 10, 50), ("c2", 32, 750, 29, 50, 200), ("b128", 128, 750, 29, 50, 200), ("b256", 256, 750, 29, 50, 200),
         ("b1024", 1024, 750, 29, 50, 200), ("b4096", 4096, 750, 29, 50, 200), ("b8192", 8192, 750, 29, 50, 200),
         ("c4", 1024, 1500, 29, 50, 200), ("L200", 2048, 750, 29, 200, 200), ("L60", 2048, 750, 29, 60, 60),
     ]
@@ -94,15 +94,16 @@ def main():
     for name, B, T, V, lmin, lmax in cfgs:
         acts, labels, al, ll = problem(B, T, V, lmin, lmax)
         dbg = torch.zeros(B, 16, dtype=torch.int64, device="cuda")
-        for mode in ("throughput", "throughput8", "latency"):
+        for mode in ("throughput", "throughput8", "latency", "latency3"):
             if mode == "latency" and B > 4096:
                 continue
-            for want_grad in ((True, False) if mode != "throughput8" else (True,)):
+            for want_grad in ((True, False) if mode not in ("throughput8", "latency3") else (True,)):
                 try:
                     warm_gpu(0.2)
                     with ClockSampler() as cs:
-                        med, best = time_call(lambda: ctc_loss_raw(acts, labels, al, ll, want_grad=want_grad, mode=mode), flush=flush)
-                    ctc_loss_raw(acts, labels, al, ll, want_grad=want_grad, mode=mode, debug=dbg)
+                        kw = dict(mode="latency", bidirectional=False) if mode == "latency3" else dict(mode=mode)
+                        med, best = time_call(lambda: ctc_loss_raw(acts, labels, al, ll, want_grad=want_grad, **kw), flush=flush)
+                    ctc_loss_raw(acts, labels, al, ll, want_grad=want_grad, debug=dbg, **kw)
                     torch.cuda.synchronize()
                     d = dbg.cpu().double()
                 except Exception as e:  # noqa: BLE001
