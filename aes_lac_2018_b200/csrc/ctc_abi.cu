@@ -35,7 +35,7 @@ ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
 // SP = 32*NS*W padded states; an utterance with L labels fits when SP >= 2L + 2.
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kBidirMaxB = 128;              // bidirectional (two sweeps + combine) path for batches up to this size
+constexpr int kBidirMaxB = 96;              // bidirectional (two sweeps + combine) path for batches up to this size
 
 const Variant *ladder_table(int ladder, int vch, int *n)
 {
@@ -377,7 +377,7 @@ ctcStatus_t run(const ctcB200Call &c)
             C.col = P.col; C.col_stride = P.col_stride; C.col_exp = P.col_exp; C.col_exp_stride = P.col_exp_stride;
             C.col_z = P.col_z; C.n = l.count;
             C.V = V; C.T_max = c.max_time; C.B = B; C.blank = c.blank_label; C.grad_scale = c.grad_scale;
-            C.frames_per_cta = 8;
+            C.frames_per_cta = 16;
             const int csm = combine_smem_bytes(l.v->sp(), V);
             if (!ensure_smem_attr((const void *)l.v->combine, csm, st)) return st;
             dim3 grid((c.max_time + C.frames_per_cta - 1) / C.frames_per_cta, l.count);

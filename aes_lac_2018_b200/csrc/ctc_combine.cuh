@@ -35,10 +35,12 @@ struct CombineParams {
 
 constexpr int kCombineThreads = 128;
 
+constexpr int kCombineWarps = kCombineThreads / 32;
+
 __host__ __device__ inline int combine_smem_bytes(int S_pad, int V)
 {
-    // prod[S_pad] floats, ptw[V+1] doubles, lab[S_pad/2] ints, pos[S_pad/2] ints, cnt[V+1], off[V+2] ints, red[8] doubles
-    return S_pad * 4 + (V + 2) * 8 + S_pad * 4 + (2 * V + 8) * 4 + 16 * 8 + 64;
+    // per warp: prod[S_pad] floats + ptw[V+2] doubles; shared: lab[S_pad/2], pos[S_pad/2], cnt[V+1], off[V+2] ints
+    return kCombineWarps * (S_pad * 4 + (V + 2) * 8) + S_pad * 4 + (2 * V + 8) * 4 + 64;
 }
 
 // NS, NT = 32*W, K: layout parameters of the sweep variant that produced the columns
@@ -52,13 +54,14 @@ __global__ void __launch_bounds__(kCombineThreads) ctc_combine_kernel(const Comb
     const int b = P.utt_ids[u];
     if (P.status[b] & (UTT_INFEASIBLE | UTT_BAD_LABEL)) return;      // cost 0 / gradient 0 already written by the sweep
     const int T = P.act_len[b], L = P.label_len[b], S = 2 * L + 1, V = P.V, blank = P.blank;
-    float *prod = (float *)smem;                           // [SP]
-    double *ptw = (double *)(prod + SP);                   // [V+2] p~ of the frame
-    int *lab = (int *)(ptw + V + 2);                       // [SP/2]
-    int *pos = lab + SP / 2;                               // [SP/2] label indices grouped by symbol
+    double *ptw_all = (double *)smem;                      // [warps][V+2] p~ of the warp's frame
+    float *prod_all = (float *)(ptw_all + kCombineWarps * (V + 2));   // [warps][SP]
+    int *lab = (int *)(prod_all + kCombineWarps * SP);     // [SP/2]
+    int *pos = lab + SP / 2;                               // [SP/2] label state indices grouped by symbol
     int *cnt = pos + SP / 2;                               // [V+1]
     int *off = cnt + V + 1;                                // [V+2]
-    double *red = (double *)(((uintptr_t)(off + V + 2) + 7) & ~(uintptr_t)7);   // [16]
+    double *ptw = ptw_all + warp * (V + 2);
+    float *prod = prod_all + warp * SP;
     const int *lab_g = P.labels + P.label_off[b];
     const float *acts_b = P.acts + (long long)b * P.act_stride_b;
     float *grads_b = P.grads + (long long)b * V;
@@ -97,49 +100,43 @@ __global__ void __launch_bounds__(kCombineThreads) ctc_combine_kernel(const Comb
     // forward and reversed sweeps must agree on log Z (each was computed from its own 750-step chain)
     if (z_ok && !(fabs(zA[2] - zB[2]) <= 1e-6 * fmax(1.0, fabs(zA[2])))) bad = 1;
 
+    // one WARP per frame (no block barrier inside the loop): softmax row, products, per-symbol sums, gradient row
     const int t_begin = blockIdx.x * P.frames_per_cta, t_end = min(T, t_begin + P.frames_per_cta);
-    for (int t = t_begin; t < t_end; ++t) {
+    for (int t = t_begin + warp; t < t_end; t += kCombineWarps) {
         // p~ of the frame, exactly as the sweeps formed it (same exp_wide, same truncation)
         const float *row = acts_b + (long long)t * P.act_stride_t;
         float m = -INFINITY;
-        for (int k = tid; k < V; k += CT) m = fmaxf(m, row[k]);
+        for (int k = lane; k < V; k += 32) m = fmaxf(m, row[k]);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (lane == 0) red[warp] = (double)m;
-        __syncthreads();
-        m = (float)fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
         if (m == -INFINITY) m = 0.f;
-        __syncthreads();
         double ssum = 0.0;
-        for (int k = tid; k < V; k += CT) {
+        for (int k = lane; k < V; k += 32) {
             const double e = __hiloint2double(__double2hiint(exp_wide(row[k] - m)), 0);
             ptw[k] = e;
             ssum += e;
         }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) ssum += shfl_xor_d(ssum, o);
-        if (lane == 0) red[4 + warp] = ssum;
+        const float rinv = 1.f / (float)ssum;
         // products alpha^_t(s) * beta^_t(s), scaled
         const double sc = scalbn(inv_z, expA[t / K] + expB[(T - 1 - t) / K] - Ea_fin);
         const unsigned *ra = colA + (long long)t * SP;
         const unsigned *rb = colB + (long long)(T - 1 - t) * SP;
-        float bsum = 0.f;
-        for (int s = tid; s < S; s += CT) {
+        float btot = 0.f;
+        for (int s = lane; s < S; s += 32) {
             const int sr = S - 1 - s;
             const double av = __hiloint2double((int)ra[(s % NS) * NT + s / NS], 0);
             const double bv = __hiloint2double((int)rb[(sr % NS) * NT + sr / NS], 0);
             const float pr = (float)(av * bv * sc);
             prod[s] = pr;
-            if (!(s & 1)) bsum += pr;
+            if (!(s & 1)) btot += pr;                       // (lane parity == state parity: even lanes own the blanks)
         }
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
-        if (lane == 0) red[8 + warp] = (double)bsum;
-        __syncthreads();
-        const float rinv = 1.f / (float)(red[4] + red[5] + red[6] + red[7]);
-        const float btot = (float)(red[8] + red[9] + red[10] + red[11]);
+        for (int o = 16; o >= 1; o >>= 1) btot += __shfl_xor_sync(0xffffffffu, btot, o);
+        __syncwarp();
         float psum = 0.f;
-        for (int k = tid; k < V; k += CT) {
+        for (int k = lane; k < V; k += 32) {
             float acc;
             if (k == blank) acc = btot;
             else {
@@ -154,11 +151,10 @@ __global__ void __launch_bounds__(kCombineThreads) ctc_combine_kernel(const Comb
         }
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, o);
-        __syncthreads();
-        if (lane == 0) red[12 + warp] = (double)psum;
-        __syncthreads();
-        if (z_ok && !(fabs(red[12] + red[13] + red[14] + red[15] - 1.0) <= 7e-6)) bad = 1;
+        if (z_ok && !(fabsf(psum - 1.f) <= 7e-6f)) bad = 1;
+        __syncwarp();
     }
+    bad = __syncthreads_or(bad);
     if (bad && tid == 0) atomicOr(&P.status[b], UTT_RANGE);
 }
 
