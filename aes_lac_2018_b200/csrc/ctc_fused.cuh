@@ -97,17 +97,26 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
     l.off_pstg = o;  o += pimg_bytes(K, V);                 // image buffer 1 (the backward sweep alternates)
     o = (o + 7) & ~7;
     l.off_acol = o;  o += K * SP * 4;                       // [K][NS][NT] 32-bit: alpha high words, then float products
-    l.off_bpart = o; o += K * (NT + 32) * 4;                // [K][NT + RB] floats: per-thread blank posterior mass
+    const int G = (NT / K) < 32 ? (NT / K) : 32;            // lanes per softmax row / per blank-reduction row
+    const int pad = (G < 32) ? G : 1;                       // row strides == G (mod 32): conflict-free (see kernel)
+    l.off_bpart = o; o += K * (NT + pad) * 4;               // [K][NT + pad] floats: per-thread blank posterior mass
     l.off_btot = o;  o += ((K + 1) & ~1) * 4;               // [K] floats
-    l.off_cks = o;   o += SP * 8;                           // staged checkpoint column [NS][NT] doubles
     l.off_dbg = o;   o += 16 * 8;                           // phase cycle counters (profiling aid)
     l.off_xch = o;   o += 2 * W * 2 * 8;
     l.off_zfin = o;  o += 2 * 8 + 32 * 8;                   // zfin[2] + per-warp logsum
-    l.off_raw = o;   o += K * (VP + 32) * 4;                // [K][VP + G] staged raw activations, pad columns = -inf
+    // One region, two lives: the staged raw rows (forward sweep only), the label list and the per-label product
+    // slots (prologue only) are all dead when the backward sweep starts, which is when the staged checkpoint
+    // column (cp.async target, backward sweep only) comes alive.
+    l.off_cks = o;                                          // [NS][NT] doubles, backward sweep
+    l.off_raw = o;                                          // [K][VP + pad] floats, forward sweep
+    l.off_lab = l.off_raw + K * (VP + pad) * 4;             // [LP] ints, prologue
+    l.off_slot = l.off_lab + LP * 4;                        // [LP] ints, prologue
+    {
+        const int a = K * (VP + pad) * 4 + 2 * LP * 4, b = SP * 8;
+        o += ((a > b ? a : b) + 7) & ~7;
+    }
     l.off_ea = o;    o += (nC + 1) * 4;
-    l.off_lab = o;   o += LP * 4;
-    l.off_pos = o;   o += LP * 4;
-    l.off_slot = o;  o += LP * 4;                           // product slot of every label position
+    l.off_pos = o;   o += LP * 4;                           // list mode: product slots grouped by symbol (gather)
     l.off_cnt = o;   o += (V + 1) * 4;
     l.off_off = o;   o += (V + 1) * 4;
     l.off_misc = o;  o += 8 * 4;
