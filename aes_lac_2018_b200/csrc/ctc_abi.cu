@@ -116,8 +116,11 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     std::vector<int> cls(B);
     std::vector<int> count(nl, 0);
     int t_min = 0x7fffffff, t_max = 0;
+    // Small batches (bidirectional path): one variant for everybody -- the per-step latency of the latency ladder
+    // barely depends on the variant, while every extra bucket costs two more launches and a stream fork/join.
+    const bool one_bucket = (mode == 2) && want_grad && B <= kBidirMaxB;
     for (int b = 0; b < B; ++b) {
-        const Variant *v = pick(ladder, nl, label_len[b]);
+        const Variant *v = pick(ladder, nl, one_bucket ? max_L : label_len[b]);
         if (!v) return fail(CTC_STATUS_UNKNOWN_ERROR, "no kernel variant for this label length");
         cls[b] = (int)(v - ladder);
         ++count[cls[b]];
