@@ -470,6 +470,8 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
 #pragma unroll
         for (int ps = 0; ps < NPASS; ++ps) {
             const int r = tid / G + ps * RP;
+            if (RP > K && r >= K) continue;                 // more row slots than rows (W = 8, K = 4): whole warps idle;
+                                                            // writing row r >= KP would land in the next symbol's row
             const float *row = raw + r * RS + g;
             unsigned *pcol = ptab + g * KP + r;
             float x[EPT];
@@ -554,6 +556,17 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     issue_loads(0);
     phase(0);                                               // 0: prologue (labels, lists)
     for (int c = 0; c < nC; ++c) {
+        {   // a holds column t = cK-1.  States below S - 2(T - t) can no longer reach the end of the transcript:
+            // their mass only ever flows into other such states, so zeroing them here (once per chunk) is exact --
+            // and it keeps them out of the column max.  With T close to L they would otherwise dominate it (they
+            // are the paths that lag behind, free to follow the likeliest symbols) and push the live states below
+            // the fp64 range after a few hundred frames.
+            const int lo = S - 2 * (T - c * K + 1);
+            if (lo > 0) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) if (tid * NS + i < lo) a[i] = 0.0;
+            }
+        }
         rescale<NS, W>(a, Ea, scratch, warp, lane);
         if (want_grad) {
 #pragma unroll
@@ -801,6 +814,14 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             const float dev = (float)(psum0 - ((W == 1 || warp == 0) ? (double)n : 0.0));   // warp 0 carries the "- n"
             if (W == 1) chk_dev = fmaxf(chk_dev, (dev == dev) ? fabsf(dev) : INFINITY);
             else if (lane == 0) atomicAdd(chk_acc, dev);
+        }
+        {   // bt holds column t0.  States above 2*t0 + 1 cannot be reached from the start (alpha is 0 there) and only
+            // feed other such states: zero them for the same reason as the lagging alpha states in the forward sweep.
+            const int hi = 2 * t0 + 1;
+            if (hi < S - 1) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) if (tid * NS + i > hi) bt[i] = 0.0;
+            }
         }
         rescale<NS, W>(bt, Eb, scratch, warp, lane);       // (contains the barriers that order chk_acc)
         if (W > 1 && tid == 0 && z_ok) {

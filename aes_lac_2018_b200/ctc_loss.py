@@ -50,7 +50,8 @@ def _grow_workspace(lib, key, label_lens_h, act_lens_h, V, B, T, want_grad, devi
 
 def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 0, want_grad: bool = True,
                  grad_scale: float = 1.0, mode: str = "auto", debug: torch.Tensor | None = None,
-                 serial_launches: bool = False, timing: dict | None = None, bidirectional: bool = True):
+                 serial_launches: bool = False, timing: dict | None = None, bidirectional: bool = True,
+                 no_fallback: bool = False):
     """Runs the CUDA engine once.  Returns (costs[B] float32 CPU tensor, grads[T,B,V] CUDA tensor or None,
     status[B] int32 CPU tensor).  `acts` may be any T x B x V view whose last stride is 1."""
     lib = _lib.load()
@@ -112,6 +113,8 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
             call.flags |= _lib.FLAG_SERIAL_LAUNCHES
         if not bidirectional:
             call.flags |= _lib.FLAG_NO_BIDIR
+        if no_fallback:
+            call.flags |= _lib.FLAG_NO_FALLBACK
         st = lib.ctc_b200_compute(ctypes.byref(call))
         if st != _lib.CTC_STATUS_SUCCESS and b"workspace too small" in lib.ctc_b200_last_error():
             workspace = _dev_ws[key] = _grow_workspace(lib, key, label_lens_h, act_lens_h, V, B, T, want_grad, acts_d.device)

@@ -75,7 +75,9 @@ def ctc_single(acts_tv, labels, blank=0, K=16, hiword=False):
     Ea = -TA
     ckpt, Ea_c = [], []
     logsum = 0.0
+    sidx = np.arange(S)
     for c in range(nC):
+        a = np.where(sidx < S - 2 * (T - c * K + 1), 0.0, a)   # states that can no longer reach the end
         a, de = _rescale(a, TA)
         Ea += de
         ckpt.append(a.copy())
@@ -110,6 +112,7 @@ def ctc_single(acts_tv, labels, blank=0, K=16, hiword=False):
             with np.errstate(divide="ignore", invalid="ignore"):
                 post = np.where(pt32[t] > 0, (acc * sc).astype(np.float32) / pt32[t], 0.0)
             grad[t] = p32 - post.astype(np.float32)
+        b = np.where(sidx > 2 * t0 + 1, 0.0, b)               # states the start cannot reach
         b, de = _rescale(b, TB)
         Eb += de
     return float(cost), grad

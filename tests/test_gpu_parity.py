@@ -78,6 +78,10 @@ SYNTH = {
     "short_labels": dict(seed=16, T=64, B=40, V=29, lmin=0, lmax=12, tmin=20),
     "long_t3000_l600": dict(seed=17, T=3000, B=2, V=29, lmin=600, lmax=600),
     "wide_l1000": dict(seed=18, T=2100, B=1, V=29, lmin=1000, lmax=1000),
+    "widest_l2047": dict(seed=19, T=2200, B=1, V=29, lmin=2047, lmax=2047),
+    "wide_l1100_tight": dict(seed=21, T=1200, B=2, V=29, lmin=1100, lmax=1100),
+    "wide_l1500_v64": dict(seed=22, T=1700, B=1, V=64, lmin=1500, lmax=1500),
+    "tiny_alphabet_v2": dict(seed=20, T=40, B=3, V=2, lmin=0, lmax=12),
 }
 
 
