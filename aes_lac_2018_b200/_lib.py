@@ -83,7 +83,8 @@ class CtcB200HostCall(ctypes.Structure):
 
 EXPORTS = ("get_warpctc_version", "ctcGetStatusString", "compute_ctc_loss", "get_workspace_size",
            "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info",
-           "ctc_b200_workspace_size_host", "ctc_b200_compute_host", "ctc_b200_greedy_decode")
+           "ctc_b200_workspace_size_host", "ctc_b200_compute_host", "ctc_b200_greedy_decode",
+           "ctc_b200_edit_distance")
 
 _lib = None
 
@@ -128,6 +129,11 @@ def load() -> ctypes.CDLL:
     lib.ctc_b200_greedy_decode.argtypes = [
         ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.ctc_b200_edit_distance.restype = ctypes.c_int
+    lib.ctc_b200_edit_distance.argtypes = [
+        ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p]
     lib.ctc_b200_compute.restype = ctypes.c_int
     lib.ctc_b200_compute.argtypes = [ctypes.POINTER(CtcB200Call)]
     _lib = lib

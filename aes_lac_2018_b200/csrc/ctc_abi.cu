@@ -14,6 +14,7 @@
 
 #include "../../include/ctc.h"
 #include "ctc_decode.cuh"
+#include "ctc_editdist.cuh"
 #include "ctc_logspace.cuh"
 #include "ctc_variants.h"
 
@@ -693,6 +694,47 @@ ctcStatus_t ctc_b200_greedy_decode(const float *probs, long long stride_b, long 
     ++g_launches;
     ctcStatus_t st = CTC_STATUS_SUCCESS;
     if (!check(cudaGetLastError(), "decode launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t ctc_b200_edit_distance(const int *hyp_tokens_device, long long hyp_stride, const int *hyp_counts_device,
+                                   int max_hyp, const int *refs_device, const int *ref_offsets_device,
+                                   const int *ref_lengths_device, int max_ref, int minibatch, int space_label, int mode,
+                                   int *distances_device, int *normalisers_device, CUstream stream)
+{
+    if (!hyp_tokens_device || !hyp_counts_device || !refs_device || !ref_offsets_device || !ref_lengths_device ||
+        !distances_device)
+        return fail(CTC_STATUS_INVALID_VALUE, "null pointer argument");
+    if (minibatch <= 0 || max_hyp < 0 || max_ref < 0) return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
+    if (mode != EDIT_TOKENS && mode != EDIT_CER && mode != EDIT_WER)
+        return fail(CTC_STATUS_INVALID_VALUE, "mode must be 0 (tokens), 1 (CER) or 2 (WER)");
+    if (max_ref > 2047) return fail(CTC_STATUS_UNKNOWN_ERROR, "references above 2047 tokens are not supported by this build");
+    EditParams E;
+    E.hyp = hyp_tokens_device; E.hyp_stride = hyp_stride; E.hyp_len = hyp_counts_device;
+    E.ref = refs_device; E.ref_off = ref_offsets_device; E.ref_len = ref_lengths_device;
+    E.dist = distances_device; E.norm = normalisers_device;
+    E.B = minibatch; E.space = space_label; E.mode = mode; E.max_hyp = max_hyp; E.max_ref = max_ref;
+    const int smem = editdist_smem_bytes(max_hyp, max_ref, mode);
+    if (smem > 200 * 1024) return fail(CTC_STATUS_UNKNOWN_ERROR, "hypothesis rows too long for the shared-memory staging");
+    cudaStream_t s = (cudaStream_t)stream;
+    ctcStatus_t st = CTC_STATUS_SUCCESS;
+    const int cols = max_ref + 1;                          // DP columns 0..max_ref, C per lane
+#define CTC_EDIT_LAUNCH(C)                                                                                           \
+    do {                                                                                                             \
+        if (smem > 48 * 1024 &&                                                                                      \
+            !check(cudaFuncSetAttribute(ctc_edit_distance_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                        smem), "edit distance smem attribute", CTC_STATUS_EXECUTION_FAILED, st))     \
+            return st;                                                                                               \
+        ctc_edit_distance_kernel<C><<<minibatch, 32, smem, s>>>(E);                                                  \
+    } while (0)
+    if (cols <= 32 * 4) CTC_EDIT_LAUNCH(4);
+    else if (cols <= 32 * 8) CTC_EDIT_LAUNCH(8);
+    else if (cols <= 32 * 16) CTC_EDIT_LAUNCH(16);
+    else if (cols <= 32 * 32) CTC_EDIT_LAUNCH(32);
+    else CTC_EDIT_LAUNCH(64);
+#undef CTC_EDIT_LAUNCH
+    ++g_launches;
+    if (!check(cudaGetLastError(), "edit distance launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     return CTC_STATUS_SUCCESS;
 }
 

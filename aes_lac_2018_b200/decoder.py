@@ -1,9 +1,12 @@
-"""GPU greedy CTC decode -- drop-in for the reference's `GreedyDecoder.decode`.
+"""GPU greedy CTC decode and WER/CER scoring -- drop-in for the reference's `GreedyDecoder`.
 
 Reference: /root/reference/codes/decoder.py:95-160 (used by codes/metrics.py:111 and test.py:78):
 `decode(probs[B,T,V], sizes) -> (strings, offsets)` where `strings[b] == [text]` and `offsets[b] == [IntTensor]`.
 There the argmax is one torch kernel but the collapse is a Python loop with one `.item()` sync per frame;
 here both happen in one sm_100a kernel (csrc/ctc_decode.cuh) and only the compacted tokens come back.
+Scoring (`wer`, `cer`, decoder.py:49-78; python-Levenshtein on host strings there) is one more kernel
+(csrc/ctc_editdist.cuh) over the device-resident token rows; `error_counts` chains decode -> WER -> CER and brings
+back four integers per utterance.
 CUDA only -- no CPU fallback.
 """
 from __future__ import annotations
@@ -12,7 +15,9 @@ import torch
 
 from . import _lib
 
-__all__ = ["GreedyDecoder", "greedy_decode_raw"]
+__all__ = ["GreedyDecoder", "greedy_decode_raw", "edit_distance_raw"]
+
+_EDIT_MODES = {"tokens": 0, "cer": 1, "wer": 2}
 
 
 def greedy_decode_raw(probs: torch.Tensor, sizes=None, blank: int = 0, want_offsets: bool = True):
@@ -46,6 +51,51 @@ def greedy_decode_raw(probs: torch.Tensor, sizes=None, blank: int = 0, want_offs
     return tokens, offsets, counts
 
 
+def edit_distance_raw(hyp_tokens: torch.Tensor, hyp_counts: torch.Tensor, refs, ref_lens, space: int = -1,
+                      mode: str = "tokens"):
+    """Levenshtein distance of every decoded row against its reference, on the GPU.
+    hyp_tokens: CUDA int32 [B, W] (row b holds hyp_counts[b] tokens -- what greedy_decode_raw returns);
+    refs: flat int tensor of the concatenated references (CPU or CUDA); ref_lens: [B] (CPU preferred: its maximum
+    sizes the kernel).  mode: 'tokens' | 'cer' (drop `space` tokens first) | 'wer' (words between `space` runs).
+    Returns CUDA int32 tensors (distances[B], normalisers[B]): normaliser = reference length (tokens, cer) or
+    reference word count (wer), the denominators of codes/metrics.py:145-160."""
+    lib = _lib.load()
+    if not hyp_tokens.is_cuda:
+        raise RuntimeError("aes_lac_2018_b200 edit distance is CUDA-only (B200-native); there is no CPU fallback")
+    if mode not in _EDIT_MODES:
+        raise ValueError("mode must be 'tokens', 'cer' or 'wer'")
+    if hyp_tokens.dim() != 2 or hyp_tokens.dtype != torch.int32:
+        raise TypeError("hyp_tokens must be an int32 B x W tensor")
+    dev = hyp_tokens.device
+    hyp = hyp_tokens if hyp_tokens.stride(1) == 1 or hyp_tokens.size(1) <= 1 else hyp_tokens.contiguous()
+    B, W = hyp.shape
+    lens = torch.as_tensor(ref_lens).reshape(-1)
+    if lens.numel() != B or hyp_counts.numel() != B:
+        raise ValueError("hyp_counts and ref_lens must have one entry per utterance")
+    lens_h = lens.to("cpu", torch.int64)
+    if (lens_h < 0).any():
+        raise ValueError("negative reference length")
+    max_ref = int(lens_h.max()) if B else 0
+    refs_t = torch.as_tensor(refs).reshape(-1)
+    if int(lens_h.sum()) != refs_t.numel():
+        raise ValueError("refs must hold exactly sum(ref_lens) entries")
+    with torch.cuda.device(dev):
+        offs = (torch.cumsum(lens_h, 0) - lens_h).to(torch.int32)
+        meta = torch.stack([offs, lens_h.to(torch.int32)]).to(dev, non_blocking=True)      # one small H2D
+        refs_d = refs_t.to(device=dev, dtype=torch.int32)
+        if refs_d.numel() == 0:
+            refs_d = torch.zeros(1, dtype=torch.int32, device=dev)
+        counts = hyp_counts.to(device=dev, dtype=torch.int32).reshape(-1).contiguous()
+        out = torch.empty((2, B), dtype=torch.int32, device=dev)
+        st = lib.ctc_b200_edit_distance(hyp.data_ptr(), hyp.stride(0), counts.data_ptr(), W, refs_d.data_ptr(),
+                                        meta[0].data_ptr(), meta[1].data_ptr(), max_ref, B, int(space),
+                                        _EDIT_MODES[mode], out[0].data_ptr(), out[1].data_ptr(),
+                                        torch.cuda.current_stream(dev).cuda_stream)
+        if st != _lib.CTC_STATUS_SUCCESS:
+            raise RuntimeError("ctc_b200_edit_distance: " + _lib.status_string(lib, st))
+    return out[0], out[1]
+
+
 class GreedyDecoder:
     """`GreedyDecoder(labels, blank_index=0).decode(probs, sizes)` with the reference's return structure.
     `labels` is the alphabet in index order (a string / list such as data/labels.en.json) or any object with an
@@ -56,6 +106,47 @@ class GreedyDecoder:
             label_encoder = list(label_encoder)
         self.label_encoder = label_encoder
         self.blank_index = blank_index
+        self.space_index = self._find_space()
+
+    def _find_space(self) -> int:
+        """Index of ' ' in the alphabet (-1 if it has none: then every transcript is a single word)."""
+        enc = self.label_encoder
+        try:
+            if hasattr(enc, "transform"):
+                return int(enc.transform([" "])[0])
+            return list(enc).index(" ")
+        except (ValueError, KeyError, IndexError):
+            return -1
+
+    # -- scoring (decoder.py:49-78) ------------------------------------------------------------------------
+    @staticmethod
+    def _score_strings(s1: str, s2: str, mode: str) -> int:
+        dev = torch.device("cuda", torch.cuda.current_device())
+        a = torch.tensor([[ord(c) for c in s1] or [0]], dtype=torch.int32, device=dev)
+        n = torch.tensor([len(s1)], dtype=torch.int32, device=dev)
+        b = torch.tensor([ord(c) for c in s2], dtype=torch.int32)
+        d, _ = edit_distance_raw(a, n, b, torch.tensor([len(s2)]), space=ord(" "), mode=mode)
+        return int(d.item())
+
+    def wer(self, s1: str, s2: str) -> int:
+        """Word-level edit distance between two space-separated sentences (decoder.py:49-66).  Words are cut at
+        runs of ' ' (the only whitespace the reference's alphabets contain)."""
+        return self._score_strings(s1, s2, "wer")
+
+    def cer(self, s1: str, s2: str) -> int:
+        """Character-level edit distance after removing spaces (decoder.py:69-78)."""
+        return self._score_strings(s1, s2, "cer")
+
+    def error_counts(self, probs, sizes, targets, target_sizes):
+        """Decode `probs` (B x T x V, CUDA) and score every utterance against its reference without leaving the
+        device: returns a dict of CPU int64 tensors [B] -- 'wer', 'words' (reference word count), 'cer', 'chars'
+        (reference length including spaces) -- i.e. what test.py:83-88 accumulates per utterance."""
+        tokens, _, counts = greedy_decode_raw(probs, sizes, self.blank_index, want_offsets=False)
+        refs, lens = _drop_blank(targets, target_sizes, self.blank_index)
+        wd, wn = edit_distance_raw(tokens, counts, refs, lens, self.space_index, "wer")
+        cd, cn = edit_distance_raw(tokens, counts, refs, lens, self.space_index, "cer")
+        res = torch.stack([wd, wn, cd, cn]).cpu().to(torch.int64)                          # one D2H
+        return {"wer": res[0], "words": res[1], "cer": res[2], "chars": res[3]}
 
     def _to_string(self, ids):
         if not ids:
@@ -76,3 +167,16 @@ class GreedyDecoder:
             strings.append([self._to_string(tok_h[b, :n].tolist())])
             offs.append([off_h[b, :n].clone().to(torch.int32)])
         return strings, offs
+
+
+def _drop_blank(targets, target_sizes, blank):
+    """convert_to_strings (decoder.py:100-121) skips blank tokens in the references too; they never occur in
+    real transcripts, so this is a host-side no-op unless one is present."""
+    t = torch.as_tensor(targets).reshape(-1).cpu()
+    lens = torch.as_tensor(target_sizes).reshape(-1).cpu().to(torch.int64)
+    keep = t != blank
+    if bool(keep.all()):
+        return t, lens
+    owner = torch.repeat_interleave(torch.arange(lens.numel()), lens)
+    new_lens = torch.zeros_like(lens).index_add_(0, owner[keep], torch.ones(int(keep.sum()), dtype=torch.int64))
+    return t[keep], new_lens

@@ -211,6 +211,26 @@ ctcStatus_t ctc_b200_greedy_decode(const float *probs, long long stride_b, long 
                                    int blank_label, int *tokens_device, int *offsets_device, int *counts_device,
                                    CUstream stream);
 
+/*
+ * Batched Levenshtein distance between decoded transcripts and their references; everything is DEVICE memory and
+ * the call only enqueues one kernel on `stream` (one warp per utterance).  Replaces Decoder.wer / Decoder.cer of
+ * the reference (/root/reference/codes/decoder.py:49-78: python-Levenshtein on host strings, called per utterance
+ * from codes/metrics.py:118 and test.py:83-84) for hypotheses that ctc_b200_greedy_decode left on the device.
+ *   hyp_tokens_device   row b at hyp_tokens_device + b*hyp_stride, hyp_counts_device[b] valid entries (<= max_hyp)
+ *   refs_device         concatenated reference token ids; reference b = ref_lengths_device[b] entries starting at
+ *                       ref_offsets_device[b]  (<= max_ref <= 2047 each)
+ *   mode                0: distance over the token ids as they are
+ *                       1: CER -- tokens equal to space_label are removed from both sides first
+ *                       2: WER -- both sides are split into words at runs of space_label; distance over words
+ *   distances_device    [minibatch] edit distance (unit costs)
+ *   normalisers_device  [minibatch] or NULL: what the reference's metric divides by (codes/metrics.py:145-160):
+ *                       reference length including spaces (modes 0, 1) / number of reference words (mode 2)
+ */
+ctcStatus_t ctc_b200_edit_distance(const int *hyp_tokens_device, long long hyp_stride, const int *hyp_counts_device,
+                                   int max_hyp, const int *refs_device, const int *ref_offsets_device,
+                                   const int *ref_lengths_device, int max_ref, int minibatch, int space_label, int mode,
+                                   int *distances_device, int *normalisers_device, CUstream stream);
+
 /* Human-readable description of the last failure on the calling thread ("" if none). */
 const char *ctc_b200_last_error(void);
 
