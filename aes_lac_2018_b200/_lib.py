@@ -84,7 +84,25 @@ class CtcB200HostCall(ctypes.Structure):
 EXPORTS = ("get_warpctc_version", "ctcGetStatusString", "compute_ctc_loss", "get_workspace_size",
            "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info",
            "ctc_b200_workspace_size_host", "ctc_b200_compute_host", "ctc_b200_greedy_decode",
-           "ctc_b200_edit_distance")
+           "ctc_b200_edit_distance", "ctc_b200_head_workspace_size", "ctc_b200_head_forward", "ctc_b200_head_backward")
+
+class CtcB200HeadForward(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("rows", ctypes.c_int), ("features", ctypes.c_int), ("classes", ctypes.c_int),
+                ("weight", ctypes.c_void_p), ("bn_weight", ctypes.c_void_p), ("bn_bias", ctypes.c_void_p),
+                ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p),
+                ("eps", ctypes.c_float), ("momentum", ctypes.c_float), ("training", ctypes.c_int), ("softmax", ctypes.c_int),
+                ("out", ctypes.c_void_p), ("save_mean", ctypes.c_void_p), ("save_invstd", ctypes.c_void_p),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p)]
+
+
+class CtcB200HeadBackward(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_void_p), ("dlogits", ctypes.c_void_p), ("rows", ctypes.c_int), ("features", ctypes.c_int),
+                ("classes", ctypes.c_int), ("weight", ctypes.c_void_p), ("bn_weight", ctypes.c_void_p),
+                ("bn_bias", ctypes.c_void_p), ("save_mean", ctypes.c_void_p), ("save_invstd", ctypes.c_void_p),
+                ("training", ctypes.c_int), ("dx", ctypes.c_void_p), ("dweight", ctypes.c_void_p),
+                ("dbn_weight", ctypes.c_void_p), ("dbn_bias", ctypes.c_void_p),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t), ("stream", ctypes.c_void_p)]
+
 
 _lib = None
 
@@ -134,6 +152,12 @@ def load() -> ctypes.CDLL:
         ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p]
+    lib.ctc_b200_head_workspace_size.restype = ctypes.c_int
+    lib.ctc_b200_head_workspace_size.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t)]
+    lib.ctc_b200_head_forward.restype = ctypes.c_int
+    lib.ctc_b200_head_forward.argtypes = [ctypes.POINTER(CtcB200HeadForward)]
+    lib.ctc_b200_head_backward.restype = ctypes.c_int
+    lib.ctc_b200_head_backward.argtypes = [ctypes.POINTER(CtcB200HeadBackward)]
     lib.ctc_b200_compute.restype = ctypes.c_int
     lib.ctc_b200_compute.argtypes = [ctypes.POINTER(CtcB200Call)]
     _lib = lib

@@ -17,7 +17,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libctc_b200.so")
 N_GROUPS = 6
-HEADERS = ["ctc_fused.cuh", "ctc_logspace.cuh", "ctc_decode.cuh", "ctc_combine.cuh", "ctc_variants.h", "ctc_variants.cu", "ctc_abi.cu", os.path.join(ROOT, "include", "ctc.h")]
+HEADERS = ["ctc_fused.cuh", "ctc_logspace.cuh", "ctc_decode.cuh", "ctc_combine.cuh", "ctc_editdist.cuh", "ctc_variants.h",
+           "ctc_variants.cu", "ctc_abi.cu", "ctc_head.cu", "ctc_internal.h", os.path.join(ROOT, "include", "ctc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -63,6 +64,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     o = os.path.join(obj_dir, "ctc_abi.o")
     objs.append(o)
     jobs.append(([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "ctc_abi.cu"), "-o", o], None))
+    o = os.path.join(obj_dir, "ctc_head.o")
+    objs.append(o)
+    jobs.append(([nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, "ctc_head.cu"), "-o", o], None))
     logs = []
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         for rc, cmd, out in ex.map(_compile, jobs):

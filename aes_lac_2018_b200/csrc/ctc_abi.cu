@@ -15,6 +15,7 @@
 #include "../../include/ctc.h"
 #include "ctc_decode.cuh"
 #include "ctc_editdist.cuh"
+#include "ctc_internal.h"
 #include "ctc_logspace.cuh"
 #include "ctc_variants.h"
 
@@ -607,6 +608,11 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
 }
 
 }  // namespace
+
+namespace ctcb200 {
+void ctcb200_set_error(const std::string &msg) { g_last_error = msg; }
+void ctcb200_count_launch() { ++g_launches; }
+}  // namespace ctcb200
 
 extern "C" {
 

@@ -1,0 +1,630 @@
+// ctc_head.cu -- the classifier head that produces the CTC activations, fused (sm_100a).
+//
+// SURVEY.md section 8(f) row 4.  Reference: /root/reference/codes/model.py:177-180 and 205-222
+//     fc = SequenceWise(Sequential(BatchNorm1d(H), Linear(H, V, bias=False)));  x = fc(x).transpose(0, 1)
+//     (eval mode: F.softmax(x, dim=-1))
+// i.e. on the N = T*B rows of the last recurrent layer's output x[N][H] (H = 800, V = 29 / 43):
+//     training:  mu, var = batch statistics over the N rows;   y = (x - mu) / sqrt(var + eps) * gamma + beta
+//     logits = y W^T                                            (W is V x H)
+// PyTorch runs this as 3 kernels over x-sized tensors forward and 5 backward.  Here, with V <= 64 the op is a
+// *skinny* product -- 2*V flops per 4 bytes of x, far below the tensor-core ridge and close to the fp32 FMA
+// ridge -- so it is organised around reading x as few times as possible, in plain fp32 FMAs (the reference
+// computes in fp32; no tf32/bf16 rounding is introduced):
+//
+//   forward   head_stats_kernel   one pass over x: per-feature sum / sum of squares (shifted by row 0, fp64 merge)
+//             head_fold_kernel    BatchNorm's scale folded into the weights: Wk[h][v] = W[v][h] * gamma_h * invstd_h;
+//                                 running statistics updated
+//             head_bias_kernel    bias'[v] = sum_h W[v][h] * beta_h
+//             head_fwd_kernel     one pass over x: logits = (x - mu) Wk + bias'.  The mean is subtracted from the
+//                                 staged tile, NOT folded into the bias: with |mu| >> sigma the folded form cancels
+//                                 catastrophically in fp32 (64-row tiles, cp.async double buffer,
+//                                 4 x VP/8 register tile), optional row softmax in the epilogue (eval mode);
+//                                 rows are written in T x B x V order -- exactly what ctc_fused_kernel reads
+//   backward  head_colsum_kernel  s[v] = sum_n dlogits[n][v]
+//             head_wgrad_kernel   one pass over x: G[v][h] = sum_n dlogits[n][v] * (x[n][h] - mu_h)  (per-row-block
+//                                 partials, reduced in a fixed order => deterministic)
+//             head_reduce_kernel, head_finalize_kernel  from G and s alone: dW, dgamma, dbeta and the per-feature coefficients
+//                                 of dx = A_h * (dlogits W)[n][h] + B_h + C_h * (x[n][h] - mu_h)   (BatchNorm's backward
+//                                 needs only column reductions that are linear in G and s)
+//             head_dgrad_kernel   one pass over x: dx as above
+// => x is read 2x forward and 2x backward and dx written once; nothing else of size N x H exists.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/ctc.h"
+#include "ctc_internal.h"
+
+namespace ctcb200 {
+
+__device__ __forceinline__ void hd_cp_async16(void *smem_dst, const void *gsrc)
+{
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void hd_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void hd_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------
+// batch statistics: sums[0][h] = sum_n (x[n][h] - x[0][h]),  sums[1][h] = sum_n (x[n][h] - x[0][h])^2
+// (shifting by the first row removes the cancellation of E[x^2] - E[x]^2 for features with a large mean)
+__global__ void __launch_bounds__(256) head_stats_kernel(const float *__restrict__ x, int N, int H, int rows_per_cta,
+                                                         double *__restrict__ sums)
+{
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    const int H4 = H >> 2;
+    for (int h4 = threadIdx.x; h4 < H4; h4 += blockDim.x) {
+        const float4 sh = __ldg((const float4 *)x + h4);
+        double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+        for (int rb = r0; rb < r1; rb += 32) {             // fp32 partials over 32 rows, merged in fp64
+            float a[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+            const int re = min(r1, rb + 32);
+            for (int r = rb; r < re; r += 8) {             // 8 independent row loads in flight per thread
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    v[u] = (r + u < re) ? __ldg((const float4 *)(x + (size_t)(r + u) * H) + h4) : sh;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float d0 = v[u].x - sh.x, d1 = v[u].y - sh.y, d2 = v[u].z - sh.z, d3 = v[u].w - sh.w;
+                    a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
+                    q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { s1[i] += (double)a[i]; s2[i] += (double)q[i]; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            atomicAdd(&sums[h4 * 4 + i], s1[i]);
+            atomicAdd(&sums[H + h4 * 4 + i], s2[i]);
+        }
+    }
+}
+
+// fold BatchNorm into the weights; one thread per feature
+__global__ void head_fold_kernel(const float *__restrict__ x, const double *__restrict__ sums, int N, int H, int V, int VP,
+                                 const float *__restrict__ gamma, const float *__restrict__ beta,
+                                 float *__restrict__ running_mean, float *__restrict__ running_var, float eps,
+                                 float momentum, int training, const float *__restrict__ W, float *__restrict__ wk,
+                                 float *__restrict__ shift, float *__restrict__ save_mean, float *__restrict__ save_invstd)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const bool first = (blockIdx.y == 0);                  // blockIdx.y = slice of 8 classes; slice 0 also owns the statistics
+    double mean, var;
+    if (training) {
+        const double m1 = sums[h] / N;
+        mean = (double)x[h] + m1;
+        var = fmax(sums[H + h] / N - m1 * m1, 0.0);        // biased, as BatchNorm normalises with
+        if (running_mean && first) {                       // ... and unbiased into the running estimate
+            const double unb = (N > 1) ? var * ((double)N / (double)(N - 1)) : var;
+            running_mean[h] = (float)((1.0 - momentum) * running_mean[h] + momentum * mean);
+            running_var[h] = (float)((1.0 - momentum) * running_var[h] + momentum * unb);
+        }
+    } else {
+        mean = running_mean[h];
+        var = running_var[h];
+    }
+    const double invstd = 1.0 / sqrt(var + (double)eps);
+    const double g = gamma ? (double)gamma[h] : 1.0, bt = beta ? (double)beta[h] : 0.0;
+    const double scale = g * invstd;
+    if (first) {
+        shift[h] = (float)bt;
+        if (save_mean) save_mean[h] = (float)mean;
+        if (save_invstd) save_invstd[h] = (float)invstd;
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int v = blockIdx.y * 8 + j;
+        o[j] = (v < V) ? (float)((double)W[(size_t)v * H + h] * scale) : 0.f;
+    }
+    float4 *dst = (float4 *)(wk + (size_t)h * VP + blockIdx.y * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+}
+
+// bias'[v] = sum_h W[v][h] * shift[h]; one CTA per class
+__global__ void __launch_bounds__(256) head_bias_kernel(const float *__restrict__ W, const float *__restrict__ shift, int H,
+                                                        int V, float *__restrict__ bias)
+{
+    __shared__ double red[8];
+    const int v = blockIdx.x;
+    double s = 0.0;
+    if (v < V)
+        for (int h = threadIdx.x; h < H; h += 256) s += (double)W[(size_t)v * H + h] * (double)shift[h];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        bias[v] = (float)t;                                // classes v >= V get 0
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// logits[n][v] = sum_h x[n][h] * wk[h][v] + bias[v]   (+ row softmax)
+template <int VP>
+__global__ void __launch_bounds__(128) head_fwd_kernel(const float *__restrict__ x, const float *__restrict__ wk,
+                                                       const float *__restrict__ bias, const float *__restrict__ mean,
+                                                       float *__restrict__ out, int N, int H, int V, int softmax)
+{
+    constexpr int BM = 64, BK = 32, XS = BK + 4, TN = VP / 8;
+    __shared__ __align__(16) float xs[2][BM][XS];
+    __shared__ __align__(16) float ws[2][BK][VP];
+    const int tid = threadIdx.x, tr = tid >> 3, tc = tid & 7;      // rows tr + 16 i, columns tc*TN .. +TN-1
+    const int n0 = blockIdx.x * BM;
+    float acc[4][TN];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    const int nk = (H + BK - 1) / BK;
+
+    auto load_tile = [&](int kt, int buf) {
+        const int k0 = kt * BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 128, r = idx >> 3, c4 = idx & 7;
+            const int n = n0 + r, k = k0 + c4 * 4;
+            float *dst = &xs[buf][r][c4 * 4];
+            if (n < N && k < H) hd_cp_async16(dst, x + (size_t)n * H + k);
+            else *(float4 *)dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int idx = tid; idx < BK * VP / 4; idx += 128) {
+            const int kk = idx / (VP / 4), c4 = idx % (VP / 4);
+            float *dst = &ws[buf][kk][c4 * 4];
+            if (k0 + kk < H) hd_cp_async16(dst, wk + (size_t)(k0 + kk) * VP + c4 * 4);
+            else *(float4 *)dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        hd_commit();
+    };
+
+    load_tile(0, 0);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int buf = kt & 1;
+        if (kt + 1 < nk) { load_tile(kt + 1, buf ^ 1); hd_wait<1>(); }
+        else hd_wait<0>();
+        {   // centre the tile: every thread fixes up the 4 float4 it copied itself (its own cp.async have landed)
+            const int c4 = tid & 7, k = kt * BK + c4 * 4;
+            if (k < H) {
+                const float4 mu = __ldg((const float4 *)(mean + k));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 *p = (float4 *)&xs[buf][(tid + i * 128) >> 3][c4 * 4];
+                    float4 v = *p;
+                    v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
+                    *p = v;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+            float4 xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = *(const float4 *)&xs[buf][tr + 16 * i][k4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float wv[TN];
+#pragma unroll
+                for (int j4 = 0; j4 < TN; j4 += 4) {
+                    const float4 w4 = *(const float4 *)&ws[buf][k4 + kk][tc * TN + j4];
+                    wv[j4] = w4.x; wv[j4 + 1] = w4.y; wv[j4 + 2] = w4.z; wv[j4 + 3] = w4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xk = (kk == 0) ? xv[i].x : (kk == 1) ? xv[i].y : (kk == 2) ? xv[i].z : xv[i].w;
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xk, wv[j], acc[i][j]);
+                }
+            }
+        }
+        __syncthreads();                                   // the next iteration refills the other buffer
+    }
+
+    float bv[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) bv[j] = bias[tc * TN + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + tr + 16 * i;
+        float val[TN];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) val[j] = acc[i][j] + bv[j];
+        if (softmax) {                                     // the 8 lanes tc = 0..7 of a row are adjacent lanes
+            float m = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) if (tc * TN + j < V) m = fmaxf(m, val[j]);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                val[j] = (tc * TN + j < V) ? expf(val[j] - m) : 0.f;
+                s += val[j];
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float inv = 1.f / s;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) val[j] *= inv;
+        }
+        if (n < N) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j)
+                if (tc * TN + j < V) out[(size_t)n * V + tc * TN + j] = val[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_colsum_kernel(const float *__restrict__ dl, int N, int V, int rows_per_cta,
+                                                          double *__restrict__ s)
+{
+    // thread -> (row lane, class): 256 threads cover 256 / VPc rows at a time
+    const int VPc = (V <= 32) ? 32 : 64;
+    const int v = threadIdx.x % VPc, rl = threadIdx.x / VPc, RL = 256 / VPc;
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+    double acc = 0.0;
+    if (v < V) {
+        float a = 0.f;
+        int cnt = 0;
+        for (int r = r0 + rl; r < r1; r += RL) {
+            a += dl[(size_t)r * V + v];
+            if (++cnt == 64) { acc += (double)a; a = 0.f; cnt = 0; }
+        }
+        acc += (double)a;
+        atomicAdd(&s[v], acc);
+    }
+}
+
+// part[rb][v][h] = sum over the rows of block rb of dl[n][v] * x[n][h]
+template <int VP>
+__global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dl,
+                                                         const float *__restrict__ mean, float *__restrict__ part, int N,
+                                                         int H, int V, int rows_per_block)
+{
+    constexpr int BR = 16, BH = 128, TV = VP / 8;
+    __shared__ __align__(16) float xs[2][BR][BH];
+    __shared__ __align__(16) float ds[2][BR][VP];
+    const int tid = threadIdx.x, tv = tid >> 4, th = tid & 15;     // classes tv*TV.., features th*4.. and 64 + th*4..
+    const int h0 = blockIdx.x * BH;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(N, r0 + rows_per_block);
+    float acc[TV][8];
+#pragma unroll
+    for (int i = 0; i < TV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    const int nt = (r1 - r0 + BR - 1) / BR;
+
+    auto load_tile = [&](int t, int buf) {
+        const int rb = r0 + t * BR;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                      // 16 rows x 32 float4
+            const int idx = tid + i * 128, r = idx >> 5, c4 = idx & 31;
+            const int n = rb + r, h = h0 + c4 * 4;
+            float *dst = &xs[buf][r][c4 * 4];
+            if (n < r1 && h < H) hd_cp_async16(dst, x + (size_t)n * H + h);
+            else *(float4 *)dst = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        hd_commit();
+        for (int idx = tid; idx < BR * VP; idx += 128) {   // rows of V floats are not 16-byte aligned: plain loads
+            const int r = idx / VP, v = idx % VP;
+            const int n = rb + r;
+            ds[buf][r][v] = (n < r1 && v < V) ? __ldg(dl + (size_t)n * V + v) : 0.f;
+        }
+    };
+
+    if (nt > 0) load_tile(0, 0);
+    for (int t = 0; t < nt; ++t) {
+        const int buf = t & 1;
+        if (t + 1 < nt) { load_tile(t + 1, buf ^ 1); hd_wait<1>(); }
+        else hd_wait<0>();
+        {   // centre the tile (own copies only, see head_fwd_kernel); padding rows meet dl = 0
+            const int c4 = tid & 31, h = h0 + c4 * 4;
+            if (h < H) {
+                const float4 mu = __ldg((const float4 *)(mean + h));
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 *p = (float4 *)&xs[buf][(tid + i * 128) >> 5][c4 * 4];
+                    float4 v = *p;
+                    v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
+                    *p = v;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < BR; ++r) {
+            const float4 xa = *(const float4 *)&xs[buf][r][th * 4];
+            const float4 xb = *(const float4 *)&xs[buf][r][64 + th * 4];
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            float dv[TV];
+#pragma unroll
+            for (int i4 = 0; i4 < TV; i4 += 4) {
+                const float4 d4 = *(const float4 *)&ds[buf][r][tv * TV + i4];
+                dv[i4] = d4.x; dv[i4 + 1] = d4.y; dv[i4 + 2] = d4.z; dv[i4 + 3] = d4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TV; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *pp = part + (size_t)blockIdx.y * VP * H;
+#pragma unroll
+    for (int i = 0; i < TV; ++i) {
+        const int v = tv * TV + i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int h = h0 + ((j < 4) ? th * 4 + j : 64 + th * 4 + (j - 4));
+            if (h < H) pp[(size_t)v * H + h] = acc[i][j];
+        }
+    }
+}
+
+// reduce the row-block partials in a fixed order (deterministic): one thread per (class, feature).
+// Leaves gx[v][h] = sum_n dlogits[n][v] * xhat[n][h] in the first slab of `part` and writes dW.
+__global__ void __launch_bounds__(128) head_reduce_kernel(float *__restrict__ part, int RB, int VP, const double *__restrict__ s,
+                                                          int H, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                          const float *__restrict__ invstd, float *__restrict__ dW)
+{
+    const int h = blockIdx.x * 128 + threadIdx.x, v = blockIdx.y;
+    if (h >= H) return;
+    double G = 0.0;
+    for (int rb = 0; rb < RB; ++rb) G += (double)part[((size_t)rb * VP + v) * H + h];
+    const double gx = G * (double)invstd[h];               // (G is centred: no mu * s[v] term)
+    part[(size_t)v * H + h] = (float)gx;
+    if (dW) {
+        const double g = gamma ? (double)gamma[h] : 1.0, bt = beta ? (double)beta[h] : 0.0;
+        dW[(size_t)v * H + h] = (float)(g * gx + bt * s[v]);
+    }
+}
+
+// one thread per feature: dgamma, dbeta and the coefficients of dx (BatchNorm's backward needs only these column sums)
+__global__ void head_finalize_kernel(const float *__restrict__ gxs, const double *__restrict__ s, int N, int H, int V,
+                                     const float *__restrict__ W, const float *__restrict__ gamma,
+                                     const float *__restrict__ mean, const float *__restrict__ invstd, int training,
+                                     float *__restrict__ dgamma, float *__restrict__ dbeta, float *__restrict__ coef)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const double mu = mean[h], is = invstd[h];
+    const double g = gamma ? (double)gamma[h] : 1.0;
+    double db = 0.0, dg = 0.0;
+    for (int v = 0; v < V; ++v) {
+        const double w = W[(size_t)v * H + h];
+        db += s[v] * w;
+        dg += w * (double)gxs[(size_t)v * H + h];
+    }
+    if (dgamma) dgamma[h] = (float)dg;
+    if (dbeta) dbeta[h] = (float)db;
+    // dx[n][h] = A * (dlogits W)[n][h] + B + C * (x[n][h] - mu)
+    const double A = g * is;
+    double B = 0.0, C = 0.0;
+    if (training) {                                        // batch statistics depend on x
+        C = -g * dg * is * is / N;
+        B = -A * db / N;
+    }
+    coef[h] = (float)A; coef[H + h] = (float)B; coef[2 * H + h] = (float)C; coef[3 * H + h] = (float)mu;
+}
+
+// dx[n][h] = A_h * sum_v dl[n][v] W[v][h] + B_h + C_h (x[n][h] - mu_h)
+template <int VP>
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict__ x, const float *__restrict__ dl,
+                                                         const float *__restrict__ W, const float *__restrict__ coef,
+                                                         float *__restrict__ dx, int N, int H, int V)
+{
+    constexpr int BM = 64, BH = 128;
+    __shared__ __align__(16) float wt[VP][BH];
+    __shared__ float dls[VP][BM];
+    const int tid = threadIdx.x, tr = tid >> 4, th = tid & 15;     // rows tr + 16 i; features th*4.. and 64 + th*4..
+    const int h0 = blockIdx.x * BH, n0 = blockIdx.y * BM;
+    for (int idx = tid; idx < VP * BH / 4; idx += 256) {
+        const int v = idx / (BH / 4), c4 = idx % (BH / 4);
+        const int h = h0 + c4 * 4;
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v < V && h < H) w4 = __ldg((const float4 *)(W + (size_t)v * H + h));
+        *(float4 *)&wt[v][c4 * 4] = w4;
+    }
+    for (int idx = tid; idx < BM * VP; idx += 256) {
+        const int r = idx / VP, v = idx % VP;
+        const int n = n0 + r;
+        dls[v][r] = (n < N && v < V) ? __ldg(dl + (size_t)n * V + v) : 0.f;
+    }
+    __syncthreads();
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int v = 0; v < V; ++v) {
+        const float4 wa = *(const float4 *)&wt[v][th * 4];
+        const float4 wb = *(const float4 *)&wt[v][64 + th * 4];
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float d = dls[v][tr + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(d, wv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int h = h0 + half * 64 + th * 4;
+        if (h >= H) continue;
+        const float4 A = __ldg((const float4 *)(coef + h));
+        const float4 B = __ldg((const float4 *)(coef + H + h));
+        const float4 C = __ldg((const float4 *)(coef + 2 * H + h));
+        const float4 M = __ldg((const float4 *)(coef + 3 * H + h));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int n = n0 + tr + 16 * i;
+            if (n >= N) continue;
+            const float4 xv = __ldg((const float4 *)(x + (size_t)n * H + h));
+            float4 o;
+            o.x = fmaf(A.x, acc[i][half * 4 + 0], fmaf(C.x, xv.x - M.x, B.x));
+            o.y = fmaf(A.y, acc[i][half * 4 + 1], fmaf(C.y, xv.y - M.y, B.y));
+            o.z = fmaf(A.z, acc[i][half * 4 + 2], fmaf(C.z, xv.z - M.z, B.z));
+            o.w = fmaf(A.w, acc[i][half * 4 + 3], fmaf(C.w, xv.w - M.w, B.w));
+            *(float4 *)(dx + (size_t)n * H + h) = o;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+size_t up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct HeadLayout {
+    int VP, RB, rows_per_block;
+    size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, total;
+};
+
+HeadLayout head_layout(int N, int H, int V)
+{
+    HeadLayout l;
+    l.VP = (V <= 32) ? 32 : 64;
+    const int tiles = (H + 127) / 128;
+    int rb = std::max(1, (2 * 148 + tiles - 1) / tiles);   // about two CTAs per SM for the weight-gradient pass
+    int rows = (N + rb - 1) / rb;
+    rows = std::max(16, (rows + 15) / 16 * 16);
+    l.rows_per_block = rows;
+    l.RB = (N + rows - 1) / rows;
+    size_t o = 0;
+    l.off_sums = o;   o += up(sizeof(double) * 2 * H);
+    l.off_s = o;      o += up(sizeof(double) * 64);
+    l.off_wk = o;     o += up(sizeof(float) * (size_t)H * l.VP);
+    l.off_shift = o;  o += up(sizeof(float) * H);
+    l.off_bias = o;   o += up(sizeof(float) * 64);
+    l.off_coef = o;   o += up(sizeof(float) * 4 * H);
+    l.off_mean = o;   o += up(sizeof(float) * H);
+    l.off_invstd = o; o += up(sizeof(float) * H);
+    l.off_part = o;   o += up(sizeof(float) * (size_t)l.RB * l.VP * H);
+    l.total = o;
+    return l;
+}
+
+bool ok(cudaError_t e, const char *what, ctcStatus_t &st)
+{
+    if (e == cudaSuccess) return true;
+    ctcb200_set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    st = CTC_STATUS_EXECUTION_FAILED;
+    return false;
+}
+
+ctcStatus_t bad(const char *msg)
+{
+    ctcb200_set_error(msg);
+    return CTC_STATUS_INVALID_VALUE;
+}
+
+ctcStatus_t check_shape(int N, int H, int V)
+{
+    if (N <= 0 || H <= 0 || V <= 0) return bad("non-positive size");
+    if (H % 4 != 0) return bad("features must be a multiple of 4");
+    if (V > 64) {
+        ctcb200_set_error("classes above 64 are not supported by this build");
+        return CTC_STATUS_UNKNOWN_ERROR;
+    }
+    return CTC_STATUS_SUCCESS;
+}
+
+}  // namespace
+}  // namespace ctcb200
+
+using namespace ctcb200;
+
+extern "C" {
+
+ctcStatus_t ctc_b200_head_workspace_size(int rows, int features, int classes, size_t *size_bytes)
+{
+    if (!size_bytes) return bad("null pointer argument");
+    ctcStatus_t st = check_shape(rows, features, classes);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    *size_bytes = head_layout(rows, features, classes).total;
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *c)
+{
+    if (!c || !c->x || !c->weight || !c->out || !c->workspace) return bad("null pointer argument");
+    const int N = c->rows, H = c->features, V = c->classes;
+    ctcStatus_t st = check_shape(N, H, V);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    if (!c->training && (!c->running_mean || !c->running_var)) return bad("eval mode needs the running statistics");
+    if (((uintptr_t)c->x | (uintptr_t)c->weight) & 15) return bad("x and weight must be 16-byte aligned");
+    const HeadLayout l = head_layout(N, H, V);
+    if (c->workspace_bytes < l.total) return bad("workspace too small");
+    char *ws = (char *)c->workspace;
+    double *sums = (double *)(ws + l.off_sums);
+    float *wk = (float *)(ws + l.off_wk), *shift = (float *)(ws + l.off_shift), *bias = (float *)(ws + l.off_bias);
+    float *mean = c->save_mean ? c->save_mean : (float *)(ws + l.off_mean);
+    cudaStream_t s = (cudaStream_t)c->stream;
+    if (c->training) {
+        if (!ok(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * H, s), "memset", st)) return st;
+        const int ctas = std::min((N + 31) / 32, 148 * 8);
+        const int rows = ((N + ctas - 1) / ctas + 31) / 32 * 32;
+        head_stats_kernel<<<(N + rows - 1) / rows, 256, 0, s>>>(c->x, N, H, rows, sums);
+        ctcb200_count_launch();
+    }
+    head_fold_kernel<<<dim3((H + 127) / 128, l.VP / 8), 128, 0, s>>>(c->x, sums, N, H, V, l.VP, c->bn_weight, c->bn_bias, c->running_mean,
+                                                    c->running_var, c->eps, c->momentum, c->training, c->weight, wk, shift,
+                                                    mean, c->save_invstd);
+    head_bias_kernel<<<l.VP, 256, 0, s>>>(c->weight, shift, H, V, bias);
+    if (l.VP == 32) head_fwd_kernel<32><<<(N + 63) / 64, 128, 0, s>>>(c->x, wk, bias, mean, c->out, N, H, V, c->softmax);
+    else head_fwd_kernel<64><<<(N + 63) / 64, 128, 0, s>>>(c->x, wk, bias, mean, c->out, N, H, V, c->softmax);
+    ctcb200_count_launch(); ctcb200_count_launch(); ctcb200_count_launch();
+    if (!ok(cudaGetLastError(), "head forward launch", st)) return st;
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *c)
+{
+    if (!c || !c->x || !c->dlogits || !c->weight || !c->save_mean || !c->save_invstd || !c->workspace)
+        return bad("null pointer argument");
+    const int N = c->rows, H = c->features, V = c->classes;
+    ctcStatus_t st = check_shape(N, H, V);
+    if (st != CTC_STATUS_SUCCESS) return st;
+    if (((uintptr_t)c->x | (uintptr_t)c->weight | (uintptr_t)c->dx) & 15) return bad("x, weight and dx must be 16-byte aligned");
+    const HeadLayout l = head_layout(N, H, V);
+    if (c->workspace_bytes < l.total) return bad("workspace too small");
+    char *ws = (char *)c->workspace;
+    double *sv = (double *)(ws + l.off_s);
+    float *coef = (float *)(ws + l.off_coef), *part = (float *)(ws + l.off_part);
+    cudaStream_t s = (cudaStream_t)c->stream;
+    if (!ok(cudaMemsetAsync(sv, 0, sizeof(double) * 64, s), "memset", st)) return st;
+    {
+        const int ctas = std::min((N + 63) / 64, 148 * 2);
+        const int rows = (N + ctas - 1) / ctas;
+        head_colsum_kernel<<<(N + rows - 1) / rows, 256, 0, s>>>(c->dlogits, N, V, rows, sv);
+    }
+    const dim3 gw((H + 127) / 128, l.RB);
+    if (l.VP == 32) head_wgrad_kernel<32><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+    else head_wgrad_kernel<64><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+    head_reduce_kernel<<<dim3((H + 127) / 128, V), 128, 0, s>>>(part, l.RB, l.VP, sv, H, c->bn_weight, c->bn_bias,
+                                                                c->save_invstd, c->dweight);
+    head_finalize_kernel<<<(H + 127) / 128, 128, 0, s>>>(part, sv, N, H, V, c->weight, c->bn_weight, c->save_mean,
+                                                        c->save_invstd, c->training, c->dbn_weight, c->dbn_bias, coef);
+    ctcb200_count_launch();
+    ctcb200_count_launch(); ctcb200_count_launch(); ctcb200_count_launch();
+    if (c->dx) {
+        const dim3 gd((H + 127) / 128, (N + 63) / 64);
+        if (l.VP == 32) head_dgrad_kernel<32><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V);
+        else head_dgrad_kernel<64><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V);
+        ctcb200_count_launch();
+    }
+    if (!ok(cudaGetLastError(), "head backward launch", st)) return st;
+    return CTC_STATUS_SUCCESS;
+}
+
+}  // extern "C"

@@ -231,6 +231,55 @@ ctcStatus_t ctc_b200_edit_distance(const int *hyp_tokens_device, long long hyp_s
                                    const int *ref_lengths_device, int max_ref, int minibatch, int space_label, int mode,
                                    int *distances_device, int *normalisers_device, CUstream stream);
 
+/*
+ * Classifier head that produces the CTC activations: BatchNorm1d(features) followed by Linear(features -> classes,
+ * no bias) over the rows = T*B frames of the last recurrent layer.  Replaces `self.fc` of the reference
+ * (/root/reference/codes/model.py:177-180, 199-207 and SequenceWiseClassifier, model.py:205-222): 3 + 5 PyTorch
+ * kernels over rows x features tensors become two passes over x forward and two backward.  All pointers are DEVICE
+ * memory, fp32, dense row-major; calls only enqueue work on `stream`.  classes <= 64, features % 4 == 0.
+ *   x              [rows][features]           out / dlogits   [rows][classes]  (rows in T x B order: `out` is the
+ *                                                               T x B x V tensor the CTC engine reads)
+ *   weight         [classes][features]        bn_weight, bn_bias [features] (NULL: 1 / 0)
+ *   running_mean, running_var [features]: read in eval mode; updated in training mode (momentum, unbiased variance)
+ *                  when non-NULL
+ *   training       1: batch statistics (BatchNorm training semantics), 0: running statistics
+ *   softmax        1: `out` holds softmax probabilities over the classes (the reference's eval-mode output)
+ *   save_mean, save_invstd [features] written by the forward call, consumed by the backward call
+ *   dx             [rows][features] or NULL;  dweight [classes][features], dbn_weight, dbn_bias [features] or NULL
+ * The backward call takes dlogits = dLoss/dlogits (for the CTC loss: the engine's gradient buffer, as is).
+ */
+typedef struct {
+    const float *x;
+    int rows, features, classes;
+    const float *weight;
+    const float *bn_weight, *bn_bias;
+    float *running_mean, *running_var;
+    float eps, momentum;
+    int training, softmax;
+    float *out;
+    float *save_mean, *save_invstd;
+    void *workspace;
+    size_t workspace_bytes;
+    CUstream stream;
+} ctcB200HeadForward;
+
+typedef struct {
+    const float *x, *dlogits;
+    int rows, features, classes;
+    const float *weight;
+    const float *bn_weight, *bn_bias;
+    const float *save_mean, *save_invstd;
+    int training;
+    float *dx, *dweight, *dbn_weight, *dbn_bias;
+    void *workspace;
+    size_t workspace_bytes;
+    CUstream stream;
+} ctcB200HeadBackward;
+
+ctcStatus_t ctc_b200_head_workspace_size(int rows, int features, int classes, size_t *size_bytes);
+ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *call);
+ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *call);
+
 /* Human-readable description of the last failure on the calling thread ("" if none). */
 const char *ctc_b200_last_error(void);
 
