@@ -6,7 +6,7 @@ import ctypes
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libctc_b200.so")
+LIB_PATH = os.environ.get("CTC_B200_LIB") or os.path.join(PKG, "lib", "libctc_b200.so")   # (override: kernel experiments)
 
 CTC_STATUS_SUCCESS = 0
 CTC_GPU = 1

@@ -33,6 +33,19 @@
 #include <stdint.h>
 #include <math.h>
 
+#ifndef CTC_BWD_UNROLL_WIDE
+#define CTC_BWD_UNROLL_WIDE 2          // unroll factor of the backward per-frame loops for the wide W = 1 variants (0: full)
+#endif
+#ifndef CTC_FWD_UNROLL_WIDE
+#define CTC_FWD_UNROLL_WIDE 0
+#endif
+#ifndef CTC_MINB_WIDE
+#define CTC_MINB_WIDE 0                // > 0: minimum resident CTAs per SM asked of ptxas for the wide W = 1 variants
+#endif
+#ifndef CTC_BWD_UNROLL_FROM
+#define CTC_BWD_UNROLL_FROM 12
+#endif
+
 namespace ctcb200 {
 
 constexpr int kTargetExp = 256;       // binary exponent the column max is rescaled to
@@ -224,7 +237,8 @@ __device__ __forceinline__ void rescale(double (&x)[NS], int &E, unsigned *scrat
 // gather granularity).
 // VCH: the alphabet fits 32*VCH symbols (one register-staged load per lane per row and 32-symbol slice).
 template <int NS, int W, int K, int VCH>
-__global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
+__global__ void __launch_bounds__(32 * W, (CTC_MINB_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_MINB_WIDE : 0)
+ctc_fused_kernel(const FusedParams P)
 {
     static_assert(NS % 2 == 0 && NS >= 2 && NS <= 16, "NS must be even, <= 16");
     static_assert(VCH >= 1 && VCH <= 4, "alphabet slices");
@@ -248,6 +262,9 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
     constexpr int VP = VP_;                    // padded alphabet
     constexpr int EPT = VP / G;                // softmax elements per thread
     static_assert(VP % G == 0, "softmax split");
+    // unroll factor of the per-frame loops of the backward sweep (K = fully unrolled)
+    constexpr int UB = (CTC_BWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_BWD_UNROLL_WIDE : K;
+    constexpr int UF = (CTC_FWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_FWD_UNROLL_WIDE : K;
     static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
 
     extern __shared__ __align__(16) unsigned char smem[];
@@ -586,7 +603,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         if (want_grad) store_image(c);
         phase(4);                                           // 4: fwd softmax
         const int n = min(K, T - c * K);
-#pragma unroll
+#pragma unroll UF
         for (int tt = 0; tt < K; ++tt) {
             if (tt >= n) break;
             alpha_step(a, tt, par);
@@ -689,7 +706,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
         phase(8);                                           // 8: bwd softmax
         // -- recompute alpha inside the chunk from its checkpoint --
         const int Ea_c = ea_s[c];
-#pragma unroll
+#pragma unroll UB
         for (int tt = 0; tt < K; ++tt) {
             if (tt >= n) break;
             alpha_step(a, tt, par);
@@ -709,7 +726,7 @@ __global__ void __launch_bounds__(32 * W) ctc_fused_kernel(const FusedParams P)
             if (lane == 0) { xch[(bpar * W + warp) * 2] = bt[0]; xch[(bpar * W + warp) * 2 + 1] = bt[1]; }
             __syncthreads();
         }
-#pragma unroll
+#pragma unroll UB
         for (int tt = K - 1; tt >= 0; --tt) {
             if (tt < n) {
                 double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);

@@ -27,3 +27,29 @@ p = torch.randn(4, 77, 29).cuda()
 tok, off, cnt = greedy_decode_raw(p, torch.tensor([77, 5, 0, 40], dtype=torch.int32))
 torch.cuda.synchronize()
 print("decode ok", cnt.tolist())
+# the W = 8 / K = 4 variant (more softmax row slots than rows) and a tight alignment (state pruning at chunk edges)
+widest = synth_problem(5, 1250, 1, 29, 1100, 1100)
+run("widest/throughput", *widest, mode="throughput", bidirectional=False)
+run("widest/latency", *widest, mode="latency")
+# edit distance: all three modes, ragged lengths, empty sides
+from aes_lac_2018_b200 import edit_distance_raw, SequenceWiseClassifier
+rng = np.random.default_rng(0)
+hyp = torch.tensor(rng.integers(1, 29, (5, 300)).astype(np.int32)).cuda()
+cnt = torch.tensor([300, 0, 17, 150, 299], dtype=torch.int32).cuda()
+ref_lens = torch.tensor([200, 5, 0, 130, 127])
+refs = torch.tensor(rng.integers(1, 29, int(ref_lens.sum())).astype(np.int32))
+for mode in ("tokens", "cer", "wer"):
+    d, n = edit_distance_raw(hyp, cnt, refs, ref_lens, space=28, mode=mode)
+    torch.cuda.synchronize()
+    print("edit", mode, "ok", d.tolist(), n.tolist())
+# classifier head: ragged row count, both class paddings, training and eval, backward
+for (T, B, H, V) in ((37, 3, 100, 29), (20, 2, 64, 43)):
+    head = SequenceWiseClassifier(H, V).cuda()
+    x = torch.randn(T, B, H, device="cuda", requires_grad=True)
+    out = head(x)
+    out.backward(torch.randn_like(out))
+    head.eval()
+    with torch.no_grad():
+        p = head(x)
+    torch.cuda.synchronize()
+    print("head ok", tuple(out.shape), float(p.sum()))
