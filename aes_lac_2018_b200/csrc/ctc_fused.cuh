@@ -36,6 +36,9 @@
 #ifndef CTC_BWD_UNROLL_WIDE
 #define CTC_BWD_UNROLL_WIDE 2          // unroll factor of the backward per-frame loops for the wide W = 1 variants (0: full)
 #endif
+#ifndef CTC_BWD_UNROLL_MID
+#define CTC_BWD_UNROLL_MID 0           // the same for 8 <= NS < CTC_BWD_UNROLL_FROM (0: full)
+#endif
 #ifndef CTC_FWD_UNROLL_WIDE
 #define CTC_FWD_UNROLL_WIDE 0
 #endif
@@ -263,7 +266,8 @@ ctc_fused_kernel(const FusedParams P)
     constexpr int EPT = VP / G;                // softmax elements per thread
     static_assert(VP % G == 0, "softmax split");
     // unroll factor of the per-frame loops of the backward sweep (K = fully unrolled)
-    constexpr int UB = (CTC_BWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_BWD_UNROLL_WIDE : K;
+    constexpr int UB = (CTC_BWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_BWD_UNROLL_WIDE
+                     : (CTC_BWD_UNROLL_MID > 0 && NS >= 8 && W == 1) ? CTC_BWD_UNROLL_MID : K;
     constexpr int UF = (CTC_FWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_FWD_UNROLL_WIDE : K;
     static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
 

@@ -327,3 +327,55 @@ def test_out_of_range_utterances_fall_back_to_log_space(name):
     from aes_lac_2018_b200 import ctc_loss_host
     c_h, g_h, st_h = ctc_loss_host(torch.tensor(acts).pin_memory(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), n_chunks=2)
     _assert_close(c_h.numpy().astype(np.float64), g_h.numpy().astype(np.float64), oc, og, name + "/host")
+
+
+def test_bitwise_reproducible_and_stream_safe():
+    """Same inputs -> same bits, call after call, on every path (no atomics on the result path); a call issued on a
+    side stream uses its own workspace and gives the same bits as on the default stream."""
+    from aes_lac_2018_b200 import ctc_loss_raw
+    acts, labels, al, ll = synth_problem(77, 300, 24, 29, 0, 120, tmin=200)
+    a = torch.tensor(acts).cuda()
+    args = [torch.tensor(x) for x in (labels, al, ll)]
+    side = torch.cuda.Stream()
+    for mode, bidir in (("throughput", False), ("throughput8", False), ("latency", True), ("latency", False), ("auto", True)):
+        c0, g0, s0 = ctc_loss_raw(a, *args, mode=mode, bidirectional=bidir)
+        for _ in range(3):
+            c1, g1, s1 = ctc_loss_raw(a, *args, mode=mode, bidirectional=bidir)
+            assert torch.equal(c0, c1) and torch.equal(g0, g1) and torch.equal(s0, s1), mode
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            c2, g2, s2 = ctc_loss_raw(a, *args, mode=mode, bidirectional=bidir)
+        side.synchronize()
+        assert torch.equal(c0, c2) and torch.equal(g0, g2), mode
+
+
+def test_two_threads_two_streams():
+    """Two host threads drive the engine concurrently, each on its own stream (one workspace per (device, stream))."""
+    import threading
+    from aes_lac_2018_b200 import ctc_loss_raw
+    from oracle import ctc_f64
+    probs = [synth_problem(500 + i, 120, 6, 29, 5, 40) for i in range(2)]
+    want = [ctc_f64.ctc_batch(*p) for p in probs]
+    errs = []
+
+    def work(i):
+        try:
+            torch.cuda.set_device(0)
+            s = torch.cuda.Stream()
+            acts, labels, al, ll = probs[i]
+            with torch.cuda.stream(s):
+                a = torch.tensor(acts).cuda()
+                for _ in range(20):
+                    c, g, st = ctc_loss_raw(a, torch.tensor(labels), torch.tensor(al), torch.tensor(ll))
+                s.synchronize()
+            assert np.abs(c.numpy() - want[i][0]).max() <= LOSS_RTOL * np.abs(want[i][0]).max()
+            assert np.abs(g.cpu().numpy() - want[i][1]).max() <= GRAD_ATOL
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
