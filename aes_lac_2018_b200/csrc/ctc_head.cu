@@ -8,18 +8,20 @@
 //     logits = y W^T                                            (W is V x H)
 // PyTorch runs this as 3 kernels over x-sized tensors forward and 5 backward.  Here, with V <= 64 the op is a
 // *skinny* product -- 2*V flops per 4 bytes of x, far below the tensor-core ridge and close to the fp32 FMA
-// ridge -- so it is organised around reading x as few times as possible, in plain fp32 FMAs (the reference
-// computes in fp32; no tf32/bf16 rounding is introduced):
+// ridge -- so it is organised around reading x as few times as possible.  The forward product runs on the tensor
+// cores with an error-compensated tf32 split, the backward products in fp32 FMAs (the reference computes in fp32; no
+// plain tf32/bf16 rounding is introduced anywhere):
 //
 //   forward   head_stats_kernel   one pass over x: per-feature sum / sum of squares (shifted by row 0, fp64 merge)
 //             head_fold_kernel    BatchNorm's scale folded into the weights: Wk[h][v] = W[v][h] * gamma_h * invstd_h;
 //                                 running statistics updated
 //             head_bias_kernel    bias'[v] = sum_h W[v][h] * beta_h
-//             head_fwd_kernel     one pass over x: logits = (x - mu) Wk + bias'.  The mean is subtracted from the
-//                                 staged tile, NOT folded into the bias: with |mu| >> sigma the folded form cancels
-//                                 catastrophically in fp32 (64-row tiles, cp.async double buffer,
-//                                 4 x VP/8 register tile), optional row softmax in the epilogue (eval mode);
-//                                 rows are written in T x B x V order -- exactly what ctc_fused_kernel reads
+//             head_fold_tc_kernel, head_fwd_tc_kernel (ctc_head_tc.cuh)   one pass over x on the TENSOR CORES:
+//                                 logits = (x - mu) Wk + bias' as tcgen05.mma kind::tf32 with a 3xTF32 operand split
+//                                 (fp32-level accuracy), accumulator in TMEM, bias / softmax in the tcgen05.ld epilogue.
+//                                 The mean is subtracted from the staged tile, NOT folded into the bias: with
+//                                 |mu| >> sigma the folded form cancels catastrophically in fp32.  Rows are written in
+//                                 T x B x V order -- exactly what ctc_fused_kernel reads
 //   backward  head_colsum_kernel  s[v] = sum_n dlogits[n][v]
 //             head_wgrad_kernel   one pass over x: G[v][h] = sum_n dlogits[n][v] * (x[n][h] - mu_h)  (per-row-block
 //                                 partials, reduced in a fixed order => deterministic)
@@ -36,6 +38,7 @@
 
 #include "../../include/ctc.h"
 #include "ctc_internal.h"
+#include "ctc_head_tc.cuh"
 
 namespace ctcb200 {
 
@@ -45,6 +48,14 @@ __device__ __forceinline__ void hd_cp_async16(void *smem_dst, const void *gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void hd_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+// 16-byte read-only load that ptxas may not sink next to its first use: a batch of these is issued back to back, so a
+// thread really has the whole batch in flight (with plain __ldg the compiler re-used one register and serialised them)
+__device__ __forceinline__ float4 hd_ldg_f4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 template <int N>
 __device__ __forceinline__ void hd_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -65,11 +76,12 @@ __global__ void __launch_bounds__(256) head_stats_kernel(const float *__restrict
             for (int r = rb; r < re; r += 8) {             // 8 independent row loads in flight per thread
                 float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    v[u] = (r + u < re) ? __ldg((const float4 *)(x + (size_t)(r + u) * H) + h4) : sh;
+                for (int u = 0; u < 8; ++u) v[u] = hd_ldg_f4(x + (size_t)min(r + u, re - 1) * H + h4 * 4);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const float d0 = v[u].x - sh.x, d1 = v[u].y - sh.y, d2 = v[u].z - sh.z, d3 = v[u].w - sh.w;
+                    const bool in = (r + u < re);          // (clamped rows were loaded twice: count them once)
+                    const float d0 = in ? v[u].x - sh.x : 0.f, d1 = in ? v[u].y - sh.y : 0.f;
+                    const float d2 = in ? v[u].z - sh.z : 0.f, d3 = in ? v[u].w - sh.w : 0.f;
                     a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
                     q[0] = fmaf(d0, d0, q[0]); q[1] = fmaf(d1, d1, q[1]); q[2] = fmaf(d2, d2, q[2]); q[3] = fmaf(d3, d3, q[3]);
                 }
@@ -149,122 +161,6 @@ __global__ void __launch_bounds__(256) head_bias_kernel(const float *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// logits[n][v] = sum_h x[n][h] * wk[h][v] + bias[v]   (+ row softmax)
-template <int VP>
-__global__ void __launch_bounds__(128) head_fwd_kernel(const float *__restrict__ x, const float *__restrict__ wk,
-                                                       const float *__restrict__ bias, const float *__restrict__ mean,
-                                                       float *__restrict__ out, int N, int H, int V, int softmax)
-{
-    constexpr int BM = 64, BK = 32, XS = BK + 4, TN = VP / 8;
-    __shared__ __align__(16) float xs[2][BM][XS];
-    __shared__ __align__(16) float ws[2][BK][VP];
-    const int tid = threadIdx.x, tr = tid >> 3, tc = tid & 7;      // rows tr + 16 i, columns tc*TN .. +TN-1
-    const int n0 = blockIdx.x * BM;
-    float acc[4][TN];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    const int nk = (H + BK - 1) / BK;
-
-    auto load_tile = [&](int kt, int buf) {
-        const int k0 = kt * BK;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = tid + i * 128, r = idx >> 3, c4 = idx & 7;
-            const int n = n0 + r, k = k0 + c4 * 4;
-            float *dst = &xs[buf][r][c4 * 4];
-            if (n < N && k < H) hd_cp_async16(dst, x + (size_t)n * H + k);
-            else *(float4 *)dst = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (int idx = tid; idx < BK * VP / 4; idx += 128) {
-            const int kk = idx / (VP / 4), c4 = idx % (VP / 4);
-            float *dst = &ws[buf][kk][c4 * 4];
-            if (k0 + kk < H) hd_cp_async16(dst, wk + (size_t)(k0 + kk) * VP + c4 * 4);
-            else *(float4 *)dst = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        hd_commit();
-    };
-
-    load_tile(0, 0);
-    for (int kt = 0; kt < nk; ++kt) {
-        const int buf = kt & 1;
-        if (kt + 1 < nk) { load_tile(kt + 1, buf ^ 1); hd_wait<1>(); }
-        else hd_wait<0>();
-        {   // centre the tile: every thread fixes up the 4 float4 it copied itself (its own cp.async have landed)
-            const int c4 = tid & 7, k = kt * BK + c4 * 4;
-            if (k < H) {
-                const float4 mu = __ldg((const float4 *)(mean + k));
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 *p = (float4 *)&xs[buf][(tid + i * 128) >> 3][c4 * 4];
-                    float4 v = *p;
-                    v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
-                    *p = v;
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k4 = 0; k4 < BK; k4 += 4) {
-            float4 xv[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) xv[i] = *(const float4 *)&xs[buf][tr + 16 * i][k4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                float wv[TN];
-#pragma unroll
-                for (int j4 = 0; j4 < TN; j4 += 4) {
-                    const float4 w4 = *(const float4 *)&ws[buf][k4 + kk][tc * TN + j4];
-                    wv[j4] = w4.x; wv[j4 + 1] = w4.y; wv[j4 + 2] = w4.z; wv[j4 + 3] = w4.w;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float xk = (kk == 0) ? xv[i].x : (kk == 1) ? xv[i].y : (kk == 2) ? xv[i].z : xv[i].w;
-#pragma unroll
-                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(xk, wv[j], acc[i][j]);
-                }
-            }
-        }
-        __syncthreads();                                   // the next iteration refills the other buffer
-    }
-
-    float bv[TN];
-#pragma unroll
-    for (int j = 0; j < TN; ++j) bv[j] = bias[tc * TN + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int n = n0 + tr + 16 * i;
-        float val[TN];
-#pragma unroll
-        for (int j = 0; j < TN; ++j) val[j] = acc[i][j] + bv[j];
-        if (softmax) {                                     // the 8 lanes tc = 0..7 of a row are adjacent lanes
-            float m = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) if (tc * TN + j < V) m = fmaxf(m, val[j]);
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            float s = 0.f;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) {
-                val[j] = (tc * TN + j < V) ? expf(val[j] - m) : 0.f;
-                s += val[j];
-            }
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float inv = 1.f / s;
-#pragma unroll
-            for (int j = 0; j < TN; ++j) val[j] *= inv;
-        }
-        if (n < N) {
-#pragma unroll
-            for (int j = 0; j < TN; ++j)
-                if (tc * TN + j < V) out[(size_t)n * V + tc * TN + j] = val[j];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) head_colsum_kernel(const float *__restrict__ dl, int N, int V, int rows_per_cta,
                                                           double *__restrict__ s)
 {
@@ -327,7 +223,8 @@ __global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict
         const int buf = t & 1;
         if (t + 1 < nt) { load_tile(t + 1, buf ^ 1); hd_wait<1>(); }
         else hd_wait<0>();
-        {   // centre the tile (own copies only, see head_fwd_kernel); padding rows meet dl = 0
+        {   // centre the tile: every thread fixes up the float4 it copied itself (its own cp.async have landed);
+            // padding rows meet dl = 0
             const int c4 = tid & 31, h = h0 + c4 * 4;
             if (h < H) {
                 const float4 mu = __ldg((const float4 *)(mean + h));
@@ -428,6 +325,15 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
     __shared__ float dls[VP][BM];
     const int tid = threadIdx.x, tr = tid >> 4, th = tid & 15;     // rows tr + 16 i; features th*4.. and 64 + th*4..
     const int h0 = blockIdx.x * BH, n0 = blockIdx.y * BM;
+    // the x values of this thread's 4 x 8 outputs: requested now, used in the epilogue (latency hidden by everything between)
+    float4 xq[2][4];
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int h = min(h0 + half * 64 + th * 4, H - 4), n = min(n0 + tr + 16 * i, N - 1);
+            xq[half][i] = hd_ldg_f4(x + (size_t)n * H + h);
+        }
     for (int idx = tid; idx < VP * BH / 4; idx += 256) {
         const int v = idx / (BH / 4), c4 = idx % (BH / 4);
         const int h = h0 + c4 * 4;
@@ -469,7 +375,7 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
         for (int i = 0; i < 4; ++i) {
             const int n = n0 + tr + 16 * i;
             if (n >= N) continue;
-            const float4 xv = __ldg((const float4 *)(x + (size_t)n * H + h));
+            const float4 xv = xq[half][i];
             float4 o;
             o.x = fmaf(A.x, acc[i][half * 4 + 0], fmaf(C.x, xv.x - M.x, B.x));
             o.y = fmaf(A.y, acc[i][half * 4 + 1], fmaf(C.y, xv.y - M.y, B.y));
@@ -487,7 +393,7 @@ size_t up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct HeadLayout {
     int VP, RB, rows_per_block;
-    size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, total;
+    size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, off_bc, total;
 };
 
 HeadLayout head_layout(int N, int H, int V)
@@ -495,7 +401,7 @@ HeadLayout head_layout(int N, int H, int V)
     HeadLayout l;
     l.VP = (V <= 32) ? 32 : 64;
     const int tiles = (H + 127) / 128;
-    int rb = std::max(1, (2 * 148 + tiles - 1) / tiles);   // about two CTAs per SM for the weight-gradient pass
+    int rb = std::max(1, (8 * 148 + tiles - 1) / tiles);   // about eight CTAs per SM for the weight-gradient pass
     int rows = (N + rb - 1) / rb;
     rows = std::max(16, (rows + 15) / 16 * 16);
     l.rows_per_block = rows;
@@ -510,6 +416,7 @@ HeadLayout head_layout(int N, int H, int V)
     l.off_mean = o;   o += up(sizeof(float) * H);
     l.off_invstd = o; o += up(sizeof(float) * H);
     l.off_part = o;   o += up(sizeof(float) * (size_t)l.RB * l.VP * H);
+    l.off_bc = o;     o += up(tc::head_tc_weight_bytes(H, l.VP));
     l.total = o;
     return l;
 }
@@ -572,8 +479,8 @@ ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *c)
     cudaStream_t s = (cudaStream_t)c->stream;
     if (c->training) {
         if (!ok(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * H, s), "memset", st)) return st;
-        const int ctas = std::min((N + 31) / 32, 148 * 8);
-        const int rows = ((N + ctas - 1) / ctas + 31) / 32 * 32;
+        const int ctas = std::min((N + 31) / 32, 148 * 8);     // two full waves of 4 resident CTAs per SM
+        const int rows = (N + ctas - 1) / ctas;
         head_stats_kernel<<<(N + rows - 1) / rows, 256, 0, s>>>(c->x, N, H, rows, sums);
         ctcb200_count_launch();
     }
@@ -581,9 +488,20 @@ ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *c)
                                                     c->running_var, c->eps, c->momentum, c->training, c->weight, wk, shift,
                                                     mean, c->save_invstd);
     head_bias_kernel<<<l.VP, 256, 0, s>>>(c->weight, shift, H, V, bias);
-    if (l.VP == 32) head_fwd_kernel<32><<<(N + 63) / 64, 128, 0, s>>>(c->x, wk, bias, mean, c->out, N, H, V, c->softmax);
-    else head_fwd_kernel<64><<<(N + 63) / 64, 128, 0, s>>>(c->x, wk, bias, mean, c->out, N, H, V, c->softmax);
-    ctcb200_count_launch(); ctcb200_count_launch(); ctcb200_count_launch();
+    {
+        float4 *bc = (float4 *)(ws + l.off_bc);
+        const int nk = (H + tc::kBK - 1) / tc::kBK;
+        tc::head_fold_tc_kernel<<<(nk * 8 * l.VP + 127) / 128, 128, 0, s>>>(wk, H, l.VP, bc);
+        const int smem = tc::head_tc_smem_bytes(l.VP);
+        if (l.VP == 32) {
+            if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
+            tc::head_fwd_tc_kernel<32><<<(N + 127) / 128, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
+        } else {
+            if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
+            tc::head_fwd_tc_kernel<64><<<(N + 127) / 128, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
+        }
+    }
+    for (int i = 0; i < 4; ++i) ctcb200_count_launch();    // fold, bias, fold_tc, forward
     if (!ok(cudaGetLastError(), "head forward launch", st)) return st;
     return CTC_STATUS_SUCCESS;
 }
