@@ -36,11 +36,11 @@
 #ifndef CTC_BWD_UNROLL_WIDE
 #define CTC_BWD_UNROLL_WIDE 2          // unroll factor of the backward per-frame loops for the wide W = 1 variants (0: full)
 #endif
+#ifndef CTC_ROW_LOG
+#define CTC_ROW_LOG logf               // log of a softmax row sum (kept accurate: T fast-math logs add up on a near-zero cost)
+#endif
 #ifndef CTC_BWD_UNROLL_MID
 #define CTC_BWD_UNROLL_MID 0           // the same for 8 <= NS < CTC_BWD_UNROLL_FROM (0: full)
-#endif
-#ifndef CTC_FWD_UNROLL_WIDE
-#define CTC_FWD_UNROLL_WIDE 0
 #endif
 #ifndef CTC_MINB_WIDE
 #define CTC_MINB_WIDE 0                // > 0: minimum resident CTAs per SM asked of ptxas for the wide W = 1 variants
@@ -268,7 +268,6 @@ ctc_fused_kernel(const FusedParams P)
     // unroll factor of the per-frame loops of the backward sweep (K = fully unrolled)
     constexpr int UB = (CTC_BWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_BWD_UNROLL_WIDE
                      : (CTC_BWD_UNROLL_MID > 0 && NS >= 8 && W == 1) ? CTC_BWD_UNROLL_MID : K;
-    constexpr int UF = (CTC_FWD_UNROLL_WIDE > 0 && NS >= CTC_BWD_UNROLL_FROM && W == 1) ? CTC_FWD_UNROLL_WIDE : K;
     static_assert(G >= 1 && (G & (G - 1)) == 0 && NT % K == 0 && K % TG == 0, "bad K / W combination");
 
     extern __shared__ __align__(16) unsigned char smem[];
@@ -521,7 +520,7 @@ ctc_fused_kernel(const FusedParams P)
             if (g == 0 && r < n) {
                 const float sf = bad ? NAN : (float)s;      // NaN activations poison the row (cost and gradient)
                 rinv[r] = (sf > 0.f) ? 1.f / sf : (bad ? NAN : 0.f);
-                lg += logf(sf);                     // (accurate: the T per-row errors of __logf add up to 6e-5 on a near-zero cost)
+                lg += CTC_ROW_LOG(sf);                     // (accurate: the T per-row errors of __logf add up to 6e-5 on a near-zero cost)
             }
         }
         return lg;
@@ -607,7 +606,7 @@ ctc_fused_kernel(const FusedParams P)
         if (want_grad) store_image(c);
         phase(4);                                           // 4: fwd softmax
         const int n = min(K, T - c * K);
-#pragma unroll UF
+#pragma unroll
         for (int tt = 0; tt < K; ++tt) {
             if (tt >= n) break;
             alpha_step(a, tt, par);
@@ -710,12 +709,25 @@ ctc_fused_kernel(const FusedParams P)
         phase(8);                                           // 8: bwd softmax
         // -- recompute alpha inside the chunk from its checkpoint --
         const int Ea_c = ea_s[c];
-#pragma unroll UB
-        for (int tt = 0; tt < K; ++tt) {
-            if (tt >= n) break;
+        auto recompute_frame = [&](int tt) {
             alpha_step(a, tt, par);
 #pragma unroll
             for (int i = 0; i < NS; ++i) acol[(tt * NS + i) * NT + tid] = (unsigned)__double2hiint(a[i]);
+        };
+        // (a plain `#pragma unroll` and `#pragma unroll K` are NOT the same to nvcc: the counted form keeps loop
+        //  bookkeeping and cost 20 % on the forward sweep when it was tried there -- so the full unroll stays plain)
+        if constexpr (UB == K) {
+#pragma unroll
+            for (int tt = 0; tt < K; ++tt) {
+                if (tt >= n) break;
+                recompute_frame(tt);
+            }
+        } else {
+#pragma unroll UB
+            for (int tt = 0; tt < K; ++tt) {
+                if (tt >= n) break;
+                recompute_frame(tt);
+            }
         }
         phase(9);                                           // 9: alpha recompute
         // posterior scale of this chunk: 2^(Ea_c + Eb - Ea_fin) / Z^
@@ -730,8 +742,7 @@ ctc_fused_kernel(const FusedParams P)
             if (lane == 0) { xch[(bpar * W + warp) * 2] = bt[0]; xch[(bpar * W + warp) * 2 + 1] = bt[1]; }
             __syncthreads();
         }
-#pragma unroll UB
-        for (int tt = K - 1; tt >= 0; --tt) {
+        auto beta_frame = [&](int tt) {
             if (tt < n) {
                 double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);
                 if (lane == 31) {
@@ -772,6 +783,13 @@ ctc_fused_kernel(const FusedParams P)
                     bpar ^= 1;
                 }
             }
+        };
+        if constexpr (UB == K) {
+#pragma unroll
+            for (int tt = K - 1; tt >= 0; --tt) beta_frame(tt);
+        } else {
+#pragma unroll UB
+            for (int tt = K - 1; tt >= 0; --tt) beta_frame(tt);
         }
         cta_sync<W>();                                      // products and blank partials visible
         phase(10);                                          // 10: beta steps
