@@ -177,3 +177,25 @@ def test_decoder_wer_cer_and_metrics_follow_the_reference_flow():
         assert abs(ms.compute() - sum(dist) / sum(den) * 100) < 1e-9
     with pytest.raises(RuntimeError):
         WER(dec).compute()
+
+
+# ---------------------------------------------------------------- CPU: host-side helpers of the scoring path
+def test_host_helpers_space_index_and_blank_dropping():
+    from aes_lac_2018_b200.decoder import GreedyDecoder, _drop_blank
+    assert GreedyDecoder(ALPHABET).space_index == SPACE
+    assert GreedyDecoder("_abc").space_index == -1                      # alphabet without a space
+    assert GreedyDecoder(list("_ ab")).space_index == 1
+
+    class Enc:                                                            # OrderedLabelEncoder-like object
+        def transform(self, xs):
+            return [{"_": 0, "a": 1, " ": 2}[x] for x in xs]
+    assert GreedyDecoder(Enc()).space_index == 2
+
+    t = torch.tensor([1, 2, 3, 4, 5, 6], dtype=torch.int32)
+    lens = torch.tensor([2, 0, 4], dtype=torch.int32)
+    r, l = _drop_blank(t, lens, blank=0)                                 # nothing to drop: untouched
+    assert r.tolist() == t.tolist() and l.tolist() == [2, 0, 4]
+    t = torch.tensor([0, 2, 0, 0, 5, 6, 0], dtype=torch.int32)
+    lens = torch.tensor([3, 1, 3], dtype=torch.int32)
+    r, l = _drop_blank(t, lens, blank=0)                                 # convert_to_strings skips blanks (decoder.py:127)
+    assert r.tolist() == [2, 5, 6] and l.tolist() == [1, 0, 2]
