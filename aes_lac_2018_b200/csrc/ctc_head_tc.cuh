@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kThreads) head_fwd_tc_kernel(const float *__re
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
+        __syncwarp();                                      // (.sync.aligned below: the warp must be converged after the tid == 0 block)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(VP) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }

@@ -33,8 +33,9 @@ def _ptr(t):
 
 def head_forward_raw(x, weight, bn_weight, bn_bias, running_mean, running_var, training, eps=1e-5, momentum=0.1,
                      softmax=False):
-    """x: CUDA float32 [T, B, H] (or [N, H]).  Returns (out [T, B, V], save_mean [H], save_invstd [H]); updates the
-    running statistics in place in training mode."""
+    """x: CUDA float32 [T, B, H] (or [N, H]).  Returns (out [T, B, V], save_mean [H], save_invstd [H], x2, W) where x2 / W
+    are the contiguous [N, H] / [V, H] tensors the kernels read (kept for the backward call); updates the running
+    statistics in place in training mode."""
     lib = _lib.load()
     if not x.is_cuda:
         raise RuntimeError("aes_lac_2018_b200 classifier head is CUDA-only (B200-native); there is no CPU fallback")
