@@ -125,3 +125,32 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in text.replace("float64 oracle", "").replace("the oracle", ""), f
     alias = open(os.path.join(ROOT, "warpctc_pytorch", "__init__.py")).read()
     assert "oracle" not in alias
+
+
+def test_every_call_struct_matches_the_c_header_field_by_field(tmp_path):
+    """include/ctc.h is compiled as plain C (gcc) and every field offset of the call structs is compared with the ctypes
+    mirror in aes_lac_2018_b200/_lib.py -- a mismatch would silently shift pointers in the binding."""
+    import shutil
+    import subprocess
+    from aes_lac_2018_b200 import _lib
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    pairs = [("ctcB200Call", _lib.CtcB200Call), ("ctcB200HostCall", _lib.CtcB200HostCall),
+             ("ctcB200HeadForward", _lib.CtcB200HeadForward), ("ctcB200HeadBackward", _lib.CtcB200HeadBackward)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ctc.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append(f'printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out.strip().splitlines()}
+    for cname, cls in pairs:
+        assert got[(cname, "sizeof")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, f"{cname}.{fname}"
