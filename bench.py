@@ -147,9 +147,10 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "utterances/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1] shape T={T} V={V} L~U{{{LMIN}..{LMAX}}} fp32; bounded sample of "
-                               f"{sample} utterances per step on the host CPU",
-                   "batch_per_step": sample, "T": T, "V": V},
+        "config": {"workload": f"BASELINE configs[1] shape (T={T}, V={V}, L~U{{{LMIN}..{LMAX}}}, fp32 activations, "
+                               f"randn logits) at throughput batch {args.batch} utterances per GPU",
+                   "batch_per_gpu": args.batch, "T": T, "V": V, "label_len": [LMIN, LMAX],
+                   "reference_sample": f"each step is a bounded sample of {sample} utterances of that workload on the host CPU"},
         "cpu_baseline": {"value": val, "unit": "utterances/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} utterances x {steps} steps, fp32 C/OpenMP restatement of warp-ctc's CPU path "
                                    "(oracle/warpctc_cpu.c); warp-ctc itself is not installable offline"},
