@@ -315,25 +315,43 @@ __global__ void head_finalize_kernel(const float *__restrict__ gxs, const double
 }
 
 // dx[n][h] = A_h * sum_v dl[n][v] W[v][h] + B_h + C_h (x[n][h] - mu_h)
+// One CTA owns a 128-feature slice of W (kept in shared memory) and walks `blocks_per_cta` consecutive 64-row blocks;
+// the dlogits tile and the x values of the NEXT block are requested before / right after the products of the current one.
 template <int VP>
 __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict__ x, const float *__restrict__ dl,
                                                          const float *__restrict__ W, const float *__restrict__ coef,
-                                                         float *__restrict__ dx, int N, int H, int V)
+                                                         float *__restrict__ dx, int N, int H, int V, int blocks_per_cta)
 {
-    constexpr int BM = 64, BH = 128;
+    constexpr int BM = 64, BH = 128, DQ = BM * VP / 256;          // dlogits values per thread and block
     __shared__ __align__(16) float wt[VP][BH];
     __shared__ float dls[VP][BM];
     const int tid = threadIdx.x, tr = tid >> 4, th = tid & 15;     // rows tr + 16 i; features th*4.. and 64 + th*4..
-    const int h0 = blockIdx.x * BH, n0 = blockIdx.y * BM;
-    // the x values of this thread's 4 x 8 outputs: requested now, used in the epilogue (latency hidden by everything between)
-    float4 xq[2][4];
+    const int h0 = blockIdx.x * BH;
+    const int nblk = (N + BM - 1) / BM;
+    const int b0 = blockIdx.y * blocks_per_cta, b1 = min(nblk, b0 + blocks_per_cta);
+    if (b0 >= b1) return;
+
+    auto load_x = [&](int blk, float4 (&xq)[2][4]) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < 2; ++half)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int h = min(h0 + half * 64 + th * 4, H - 4), n = min(n0 + tr + 16 * i, N - 1);
-            xq[half][i] = hd_ldg_f4(x + (size_t)n * H + h);
+            for (int i = 0; i < 4; ++i) {
+                const int h = min(h0 + half * 64 + th * 4, H - 4), n = min(blk * BM + tr + 16 * i, N - 1);
+                xq[half][i] = hd_ldg_f4(x + (size_t)n * H + h);
+            }
+    };
+    auto load_dl = [&](int blk, float (&dq)[DQ]) {
+#pragma unroll
+        for (int q = 0; q < DQ; ++q) {
+            const int idx = tid + q * 256, r = idx / VP, v = idx % VP;
+            const int n = blk * BM + r;
+            dq[q] = (n < N && v < V) ? __ldg(dl + (size_t)n * V + v) : 0.f;
         }
+    };
+    float4 xq[2][4];
+    float dq[DQ];
+    load_x(b0, xq);
+    load_dl(b0, dq);
     for (int idx = tid; idx < VP * BH / 4; idx += 256) {
         const int v = idx / (BH / 4), c4 = idx % (BH / 4);
         const int h = h0 + c4 * 4;
@@ -341,48 +359,54 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
         if (v < V && h < H) w4 = __ldg((const float4 *)(W + (size_t)v * H + h));
         *(float4 *)&wt[v][c4 * 4] = w4;
     }
-    for (int idx = tid; idx < BM * VP; idx += 256) {
-        const int r = idx / VP, v = idx % VP;
-        const int n = n0 + r;
-        dls[v][r] = (n < N && v < V) ? __ldg(dl + (size_t)n * V + v) : 0.f;
-    }
-    __syncthreads();
-    float acc[4][8];
+    for (int blk = b0; blk < b1; ++blk) {
+        const int n0 = blk * BM;
+        __syncthreads();                                   // the previous block's readers of dls are done
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    for (int v = 0; v < V; ++v) {
-        const float4 wa = *(const float4 *)&wt[v][th * 4];
-        const float4 wb = *(const float4 *)&wt[v][64 + th * 4];
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float d = dls[v][tr + 16 * i];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(d, wv[j], acc[i][j]);
+        for (int q = 0; q < DQ; ++q) {
+            const int idx = tid + q * 256;
+            dls[idx % VP][idx / VP] = dq[q];
         }
-    }
+        __syncthreads();
+        if (blk + 1 < b1) load_dl(blk + 1, dq);            // (dq is free again; lands while the products are formed)
+        float acc[4][8];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int h = h0 + half * 64 + th * 4;
-        if (h >= H) continue;
-        const float4 A = __ldg((const float4 *)(coef + h));
-        const float4 B = __ldg((const float4 *)(coef + H + h));
-        const float4 C = __ldg((const float4 *)(coef + 2 * H + h));
-        const float4 M = __ldg((const float4 *)(coef + 3 * H + h));
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int n = n0 + tr + 16 * i;
-            if (n >= N) continue;
-            const float4 xv = xq[half][i];
-            float4 o;
-            o.x = fmaf(A.x, acc[i][half * 4 + 0], fmaf(C.x, xv.x - M.x, B.x));
-            o.y = fmaf(A.y, acc[i][half * 4 + 1], fmaf(C.y, xv.y - M.y, B.y));
-            o.z = fmaf(A.z, acc[i][half * 4 + 2], fmaf(C.z, xv.z - M.z, B.z));
-            o.w = fmaf(A.w, acc[i][half * 4 + 3], fmaf(C.w, xv.w - M.w, B.w));
-            *(float4 *)(dx + (size_t)n * H + h) = o;
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int v = 0; v < V; ++v) {
+            const float4 wa = *(const float4 *)&wt[v][th * 4];
+            const float4 wb = *(const float4 *)&wt[v][64 + th * 4];
+            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float d = dls[v][tr + 16 * i];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(d, wv[j], acc[i][j]);
+            }
         }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int h = h0 + half * 64 + th * 4;
+            if (h >= H) continue;
+            const float4 A = __ldg((const float4 *)(coef + h));
+            const float4 B = __ldg((const float4 *)(coef + H + h));
+            const float4 C = __ldg((const float4 *)(coef + 2 * H + h));
+            const float4 M = __ldg((const float4 *)(coef + 3 * H + h));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int n = n0 + tr + 16 * i;
+                if (n >= N) continue;
+                const float4 xv = xq[half][i];
+                float4 o;
+                o.x = fmaf(A.x, acc[i][half * 4 + 0], fmaf(C.x, xv.x - M.x, B.x));
+                o.y = fmaf(A.y, acc[i][half * 4 + 1], fmaf(C.y, xv.y - M.y, B.y));
+                o.z = fmaf(A.z, acc[i][half * 4 + 2], fmaf(C.z, xv.z - M.z, B.z));
+                o.w = fmaf(A.w, acc[i][half * 4 + 3], fmaf(C.w, xv.w - M.w, B.w));
+                *(float4 *)(dx + (size_t)n * H + h) = o;
+            }
+        }
+        if (blk + 1 < b1) load_x(blk + 1, xq);             // used after the next block's products
     }
 }
 
@@ -536,9 +560,12 @@ ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *c)
     ctcb200_count_launch();
     ctcb200_count_launch(); ctcb200_count_launch(); ctcb200_count_launch();
     if (c->dx) {
-        const dim3 gd((H + 127) / 128, (N + 63) / 64);
-        if (l.VP == 32) head_dgrad_kernel<32><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V);
-        else head_dgrad_kernel<64><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V);
+        const int tiles = (H + 127) / 128, nblk = (N + 63) / 64;
+        const int groups = std::max(1, std::min(nblk, (148 * 6 + tiles - 1) / tiles));    // ~6 CTAs per SM in flight
+        const int bpc = (nblk + groups - 1) / groups;
+        const dim3 gd(tiles, (nblk + bpc - 1) / bpc);
+        if (l.VP == 32) head_dgrad_kernel<32><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V, bpc);
+        else head_dgrad_kernel<64><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V, bpc);
         ctcb200_count_launch();
     }
     if (!ok(cudaGetLastError(), "head backward launch", st)) return st;
