@@ -53,13 +53,6 @@ const Variant *ladder_table(int ladder, int vch, int *n)
     return nullptr;
 }
 
-const Variant *pick(const Variant *ladder, int n, int L)
-{
-    for (int i = 0; i < n; ++i)
-        if (ladder[i].max_label() >= L) return &ladder[i];
-    return nullptr;
-}
-
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct Plan {
@@ -82,7 +75,9 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     if (!label_lengths || !input_lengths) return fail(CTC_STATUS_INVALID_VALUE, "null length array");
     if (V <= 0 || B <= 0 || T_max < 0) return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
     plan.B = B; plan.T_max = T_max; plan.V = V;
-    plan.meta.assign((size_t)4 * B, 0);
+    plan.launches.clear();
+    plan.meta.resize((size_t)4 * B);                     // (every entry is written below; Plan objects are reused per thread,
+                                                         //  so this does not allocate in the steady state)
     int *label_off = plan.meta.data(), *label_len = label_off + B, *act_len = label_len + B,
         *utt_ids = act_len + B;
     long long off = 0;
@@ -115,16 +110,21 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
 
     // bucket utterances by variant (counting sort: big variants first), longest first inside a bucket when the
     // lengths are ragged (tail balance).  O(B) unless T varies.
-    std::vector<int> cls(B);
+    thread_local std::vector<int> cls, cls_of_len;       // scratch reused across calls (a fresh 32 KB+ vector per call
+    cls.resize(B);                                       //  costs more than the whole pass: mmap / page faults)
     std::vector<int> count(nl, 0);
     int t_min = 0x7fffffff, t_max = 0;
     // Small batches (bidirectional path): one variant for everybody -- the per-step latency of the latency ladder
     // barely depends on the variant, while every extra bucket costs two more launches and a stream fork/join.
     const bool one_bucket = (mode == 2) && want_grad && B <= kBidirMaxB;
+    cls_of_len.resize((size_t)max_L + 1);                // label length -> variant index, once per call
+    for (int L = 0, c = 0; L <= max_L; ++L) {
+        while (c < nl && ladder[c].max_label() < L) ++c;
+        if (c >= nl) return fail(CTC_STATUS_UNKNOWN_ERROR, "no kernel variant for this label length");
+        cls_of_len[L] = c;
+    }
     for (int b = 0; b < B; ++b) {
-        const Variant *v = pick(ladder, nl, one_bucket ? max_L : label_len[b]);
-        if (!v) return fail(CTC_STATUS_UNKNOWN_ERROR, "no kernel variant for this label length");
-        cls[b] = (int)(v - ladder);
+        cls[b] = cls_of_len[one_bucket ? max_L : label_len[b]];
         ++count[cls[b]];
         t_min = std::min(t_min, act_len[b]);
         t_max = std::max(t_max, act_len[b]);
@@ -147,10 +147,6 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
             }
         }
     }
-    struct Order { int first; };
-    std::vector<Order> order(B);                          // variant index per launch-ordered slot
-    for (int c = nl - 1; c >= 0; --c)
-        for (int i = 0; i < count[c]; ++i) order[start[c] + i].first = c;
 
     size_t o = 0;
     plan.off_meta = o;   o = align_up(o + sizeof(int) * 4 * (size_t)B, 256);
@@ -160,12 +156,11 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     plan.off_ckpt = o;
     size_t ck = 0, bd = 0;
     plan.bidir = plan.latency && want_grad && B <= kBidirMaxB;
-    for (int i = 0; i < B;) {
-        int j = i;
-        while (j < B && order[j].first == order[i].first) ++j;
-        const Variant *v = &ladder[order[i].first];
+    for (int c = nl - 1; c >= 0; --c) {                  // launch order: descending variant index
+        if (count[c] == 0) continue;
+        const Variant *v = &ladder[c];
         Plan::Launch l;
-        l.v = v; l.first = i; l.count = j - i;
+        l.v = v; l.first = start[c]; l.count = count[c];
         const int nC = (T_max + v->K - 1) / v->K;
         // per CTA: nC checkpoint columns (SP doubles each) followed by nC p~ images
         l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
@@ -182,7 +177,6 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
                         "alphabet_size / max_time too large for the shared-memory layout of this kernel");
         if (plan.bidir && (!v->combine || combine_smem_bytes(v->sp(), V) > kMaxSmem)) plan.bidir = false;
         plan.launches.push_back(l);
-        i = j;
     }
     if (plan.bidir) ck = std::max(ck, bd);
     // the checkpoint area doubles as the alpha store of the log-space fallback: keep room for one utterance
@@ -311,7 +305,7 @@ ctcStatus_t run(const ctcB200Call &c)
 
     const int B = c.minibatch, V = c.alphabet_size;
     const bool want_grad = c.gradients != nullptr;
-    Plan plan;
+    thread_local Plan plan;                              // reused per thread: no allocation in the steady state
     ctcStatus_t st = make_plan(c.label_lengths, c.input_lengths, V, B, c.max_time, want_grad,
                                (int)((c.flags >> 8) & 0x3), plan);
     if (st != CTC_STATUS_SUCCESS) return st;
@@ -645,7 +639,7 @@ ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_l
     // take the max over the ladders so that a forced mode never overruns the workspace
     size_t need = 0;
     for (int mode = 1; mode <= 3; ++mode) {
-        Plan p;
+        thread_local Plan p;
         ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
                                    want_gradients != 0, mode, p, /*size_only=*/true);
         if (st != CTC_STATUS_SUCCESS) return st;
