@@ -185,9 +185,15 @@ def main():
     import torch.distributed as dist
     from aes_lac_2018_b200 import _lib, build as _build, ctc_loss_host, ctc_loss_raw
     from aes_lac_2018_b200.distributed import all_reduce_loss
-    if local_rank == 0 and not os.path.exists(_build.LIB):
-        _build.build()          # harness convenience only (a no-op when the in-tree .so travelled with the snapshot);
-                                # the engine itself never builds or falls back -- it fails loudly
+    if not os.path.exists(_build.LIB):
+        # harness convenience only (never taken when the in-tree .so travelled with the snapshot); the engine itself
+        # never builds or falls back -- it fails loudly.  Local rank 0 builds, the other ranks wait for the file.
+        if local_rank == 0:
+            _build.build()
+        for _ in range(1800):
+            if os.path.exists(_build.LIB):
+                break
+            time.sleep(1.0)
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
