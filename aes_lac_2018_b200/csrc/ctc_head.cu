@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
 {
     constexpr int BM = 64, BH = 128, DQ = BM * VP / 256;          // dlogits values per thread and block
     __shared__ __align__(16) float wt[VP][BH];
-    __shared__ float dls[VP][BM];
+    __shared__ __align__(16) float dls[VP][BM];           // row r of the block sits at column (r % 16) * 4 + r / 16: the four
+                                                           // rows tr, tr+16, tr+32, tr+48 of a thread are one float4
     const int tid = threadIdx.x, tr = tid >> 4, th = tid & 15;     // rows tr + 16 i; features th*4.. and 64 + th*4..
     const int h0 = blockIdx.x * BH;
     const int nblk = (N + BM - 1) / BM;
@@ -364,8 +365,8 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
         __syncthreads();                                   // the previous block's readers of dls are done
 #pragma unroll
         for (int q = 0; q < DQ; ++q) {
-            const int idx = tid + q * 256;
-            dls[idx % VP][idx / VP] = dq[q];
+            const int idx = tid + q * 256, r = idx / VP;
+            dls[idx % VP][(r & 15) * 4 + (r >> 4)] = dq[q];
         }
         __syncthreads();
         if (blk + 1 < b1) load_dl(blk + 1, dq);            // (dq is free again; lands while the products are formed)
@@ -378,11 +379,12 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
             const float4 wa = *(const float4 *)&wt[v][th * 4];
             const float4 wb = *(const float4 *)&wt[v][64 + th * 4];
             const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const float4 d4 = *(const float4 *)&dls[v][tr * 4];
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float d = dls[v][tr + 16 * i];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(d, wv[j], acc[i][j]);
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], wv[j], acc[i][j]);
             }
         }
 #pragma unroll
