@@ -38,6 +38,10 @@ ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBidirMaxB = 96;              // bidirectional (two sweeps + combine) path for batches up to this size
+constexpr int kWarpMinB = 2048;             // automatic ladder choice: warp ladder from this batch size
+constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
+constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)
+constexpr int kMaxLaunches = 16;
 
 const Variant *ladder_table(int ladder, int vch, int *n)
 {
@@ -48,6 +52,8 @@ const Variant *ladder_table(int ladder, int vch, int *n)
     case 3: return ctc_variants_group3(n);
     case 4: return ctc_variants_group4(n);
     case 5: return ctc_variants_group5(n);
+    case 6: return ctc_variants_group6(n);
+    case 7: return ctc_variants_group7(n);
     }
     *n = 0;
     return nullptr;
@@ -60,11 +66,12 @@ struct Plan {
     bool latency = false;
     std::vector<int> meta;                   // [label_off B | label_len B | act_len B | utt_ids B]
     struct Launch { const Variant *v; int first, count; size_t ckpt_off; long long ckpt_stride; int smem;
-                    size_t col_off, exp_off, z_off; int exp_stride; };   // bidirectional path (column spill) offsets
+                    size_t col_off, exp_off, z_off; int exp_stride;      // bidirectional path (column spill) offsets
+                    int slots; };                                        // warp ladder: workspace slots (= max persistent CTAs)
     bool bidir = false;
     std::vector<Launch> launches;
     long long total_labels = 0;
-    size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_ckpt = 0, total = 0, ckpt_bytes = 0;
+    size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_queue = 0, off_ckpt = 0, total = 0, ckpt_bytes = 0;
     int fallback_S = 1;
 };
 
@@ -95,18 +102,21 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     }
     plan.total_labels = off;
 
-    // mode: 0 auto, 1 throughput ladder (16-step chunks), 2 latency ladder, 3 throughput ladder (8-step chunks).
-    // Auto (measured on B200, T=750, L~U{50..200}; profiles/r1_sweep_*.json): below ~2000 utterances the GPU is
-    // not full with one warp per utterance, so spend more warps per utterance (latency ladder); above, occupancy
-    // is bounded by shared memory and the 8-step chunks win.
-    if (mode == 0) mode = (B < 2048) ? 2 : 3;
-    plan.latency = (mode == 2);
-    const int vch = (V + 31) / 32;
+    // mode: 0 auto, 1 throughput ladder (16-step chunks), 2 latency ladder, 3 throughput ladder (8-step chunks),
+    // 4 warp ladder (ctc_warp.cuh: one warp per utterance, register-resident, persistent CTAs).
+    // Auto (measured on B200, T=750, L~U{50..200}; profiles/): below ~2000 utterances the GPU is not full with one
+    // warp per utterance, so spend more warps per utterance (latency ladder); above, the warp ladder wins.
+    int vch = (V + 31) / 32;
     if (vch > kMaxVch)
         return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 64 is not supported by this build");
+    const int vch_warp = V / 32 + 1;                     // the warp ladder needs one pad lane (r = 0) after the alphabet
+    if (mode == 0) mode = (B < kWarpMinB) ? 2 : 4;
+    if (mode == 4 && (vch_warp > kMaxVch || max_L > kWarpMaxLabelLen)) mode = 3;
+    plan.latency = (mode == 2);
+    if (mode == 4) vch = vch_warp;
     int nl = 0;
-    const Variant *ladder = ladder_table(mode == 2 ? LADDER_LATENCY : (mode == 3 ? LADDER_THROUGHPUT_K8 : LADDER_THROUGHPUT),
-                                         vch, &nl);
+    const Variant *ladder = ladder_table(mode == 2 ? LADDER_LATENCY : mode == 3 ? LADDER_THROUGHPUT_K8
+                                         : mode == 4 ? LADDER_WARP : LADDER_THROUGHPUT, vch, &nl);
 
     // bucket utterances by variant (counting sort: big variants first), longest first inside a bucket when the
     // lengths are ragged (tail balance).  O(B) unless T varies.
@@ -153,6 +163,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     plan.off_labels = o; o = align_up(o + sizeof(int) * (size_t)std::max<long long>(off, 1), 256);
     plan.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
     plan.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
+    plan.off_queue = o;  o = align_up(o + sizeof(int) * kMaxLaunches, 256);
     plan.off_ckpt = o;
     size_t ck = 0, bd = 0;
     plan.bidir = plan.latency && want_grad && B <= kBidirMaxB;
@@ -163,15 +174,21 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         l.v = v; l.first = start[c]; l.count = count[c];
         const int nC = (T_max + v->K - 1) / v->K;
         // per CTA: nC checkpoint columns (SP doubles each) followed by nC p~ images
-        l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
+        l.slots = l.count;
+        if (v->warp) {                                   // per resident CTA: 32-bit checkpoints, r images, 1/s
+            l.slots = std::min(l.count, kWarpSlotCap);
+            l.ckpt_stride = want_grad ? (warp_slot_words(v->NS, v->K, v->VCH, T_max) + 1) / 2 : 0;
+        } else {
+            l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
+        }
         l.ckpt_off = ck;
-        ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.count;
+        ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.slots;
         // bidirectional path: 2 slots (forward, reversed) of T_max columns of SP high words, exponents, Z
         l.exp_stride = nC + 2;
         l.col_off = bd;  bd = align_up(bd + sizeof(unsigned) * 2 * (size_t)l.count * (size_t)T_max * v->sp(), 256);
         l.exp_off = bd;  bd = align_up(bd + sizeof(int) * 2 * (size_t)l.count * l.exp_stride, 256);
         l.z_off = bd;    bd = align_up(bd + sizeof(double) * 2 * (size_t)l.count * 4, 256);
-        l.smem = make_layout(v->NS, v->W, v->K, V, T_max).total;
+        l.smem = v->warp ? make_warp_layout(v->NS, v->K, v->VCH).total : make_layout(v->NS, v->W, v->K, V, T_max).total;
         if (l.smem > kMaxSmem)
             return fail(CTC_STATUS_UNKNOWN_ERROR,
                         "alphabet_size / max_time too large for the shared-memory layout of this kernel");
@@ -247,6 +264,23 @@ bool ensure_smem_attr(const void *kernel, int smem, ctcStatus_t &st)
     return true;
 }
 
+// Persistent grid of a warp-ladder kernel: resident CTAs per SM (occupancy query, cached per kernel and device) x SMs.
+int persistent_grid(const void *kernel, int smem)
+{
+    struct Key { const void *k; int dev; int smem; int grid; };
+    thread_local std::vector<Key> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const Key &e : done)
+        if (e.k == kernel && e.dev == dev && e.smem == smem) return e.grid;
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32, smem) != cudaSuccess) per_sm = 8;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    const int grid = std::max(1, per_sm) * std::max(1, sms);
+    done.push_back(Key{kernel, dev, smem, grid});
+    return grid;
+}
+
 constexpr unsigned kFlagForceLogspace = 0x80000000u;    // internal: skip the fused kernels, log-space for every utterance
 
 // Re-run the listed utterances with the fp64 log-space kernel (ctc_logspace.cuh).  The fused kernels of this
@@ -307,7 +341,7 @@ ctcStatus_t run(const ctcB200Call &c)
     const bool want_grad = c.gradients != nullptr;
     thread_local Plan plan;                              // reused per thread: no allocation in the steady state
     ctcStatus_t st = make_plan(c.label_lengths, c.input_lengths, V, B, c.max_time, want_grad,
-                               (int)((c.flags >> 8) & 0x3), plan);
+                               (int)((c.flags >> 8) & 0x7), plan);
     if (st != CTC_STATUS_SUCCESS) return st;
     if (plan.total > c.workspace_bytes) return fail(CTC_STATUS_INVALID_VALUE, "workspace too small");
 
@@ -332,6 +366,12 @@ ctcStatus_t run(const ctcB200Call &c)
     P.V = V; P.T_max = c.max_time; P.B = B; P.blank = c.blank_label;
     P.grad_scale = c.grad_scale;
     P.debug = c.debug_device;
+    P.queue = nullptr; P.n_items = 0;
+    int *d_queue = (int *)(ws + plan.off_queue);
+    if ((int)plan.launches.size() > kMaxLaunches) return fail(CTC_STATUS_UNKNOWN_ERROR, "too many kernel variants in one call");
+    if (!plan.launches.empty() && plan.launches[0].v->warp &&
+        !check(cudaMemsetAsync(d_queue, 0, sizeof(int) * kMaxLaunches, stream), "queue memset", CTC_STATUS_MEMOPS_FAILED, st))
+        return st;
 
     const bool serial = (c.flags & CTC_B200_FLAG_SERIAL_LAUNCHES) != 0;
     AuxStreams *tim = (c.kernel_ms_host && !no_sync) ? aux_streams() : nullptr;
@@ -381,6 +421,11 @@ ctcStatus_t run(const ctcB200Call &c)
             if (!ensure_smem_attr((const void *)l.v->combine, csm, st)) return st;
             dim3 grid((c.max_time + C.frames_per_cta - 1) / C.frames_per_cta, l.count);
             l.v->combine<<<grid, kCombineThreads, csm, ls>>>(C);
+        } else if (l.v->warp) {
+            P.queue = d_queue + li; P.n_items = l.count;
+            const int grid = std::min(l.slots, persistent_grid((const void *)l.v->kernel, l.smem));
+            l.v->kernel<<<grid, 32, l.smem, ls>>>(P);
+            P.queue = nullptr; P.n_items = 0;
         } else {
             l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);
         }
@@ -638,7 +683,7 @@ ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_l
     if (!size_bytes) return fail(CTC_STATUS_INVALID_VALUE, "null size_bytes");
     // take the max over the ladders so that a forced mode never overruns the workspace
     size_t need = 0;
-    for (int mode = 1; mode <= 3; ++mode) {
+    for (int mode = 1; mode <= 4; ++mode) {
         thread_local Plan p;
         ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
                                    want_gradients != 0, mode, p, /*size_only=*/true);

@@ -84,6 +84,9 @@ struct FusedParams {
     int *col_exp;                     // [gridDim.x][col_exp_stride] alpha exponent of every chunk
     int col_exp_stride;
     double *col_z;                    // [gridDim.x][4]: Z^, Ea_fin, log Z (natural), unused
+    // --- one-warp-per-utterance kernel (ctc_warp.cuh): persistent CTAs pulling utterances from a queue ---
+    int *queue;                       // work counter (zeroed before the launch), or nullptr: CTA i does item i
+    int n_items;                      // utterances of this launch
 };
 
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------

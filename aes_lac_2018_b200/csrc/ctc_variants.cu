@@ -2,7 +2,7 @@
 #include "ctc_variants.h"
 
 #ifndef CTC_GROUP
-#error "compile with -DCTC_GROUP=<0..5>"
+#error "compile with -DCTC_GROUP=<0..7>"
 #endif
 
 namespace ctcb200 {
@@ -10,9 +10,11 @@ namespace ctcb200 {
 #define CTC_LADDER (CTC_GROUP / 2)
 #define CTC_VCH (CTC_GROUP % 2 + 1)
 #if CTC_GROUP / 2 == 2
-#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, ctc_combine_kernel<NS, W, K>}
+#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, ctc_combine_kernel<NS, W, K>, 0}
+#elif CTC_GROUP / 2 == 3
+#define VW_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp_kernel<NS, K, CTC_VCH, MAXR>, nullptr, 1}
 #else
-#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, nullptr}
+#define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, nullptr, 0}
 #endif
 
 static const Variant kTable[] = {
@@ -24,6 +26,13 @@ static const Variant kTable[] = {
     // same with 8-step chunks: half the shared memory per CTA, twice the checkpoint traffic
     V_(2, 1, 8), V_(4, 1, 8), V_(6, 1, 8), V_(8, 1, 8), V_(10, 1, 8), V_(12, 1, 8), V_(14, 1, 8), V_(16, 1, 8),
     V_(16, 2, 8), V_(16, 4, 8), V_(16, 8, 4),
+#elif CTC_LADDER == 3
+    // one warp per utterance, register-resident (ctc_warp.cuh): (NS, K, register cap per thread)
+#ifdef CTC_WARP_TABLE_INC          // kernel experiments: the table comes from a file (tools/build_alt.sh)
+#include CTC_WARP_TABLE_INC
+#else
+    VW_(2, 8, 128), VW_(4, 8, 128), VW_(6, 8, 128), VW_(8, 8, 168), VW_(10, 4, 168), VW_(12, 4, 168), VW_(14, 4, 168), VW_(16, 4, 168),
+#endif
 #else
     // latency: more warps per utterance, fewer states per thread
     V_(2, 1, 16), V_(2, 2, 16), V_(2, 4, 16), V_(4, 4, 16), V_(4, 8, 16), V_(8, 8, 8), V_(16, 8, 4),

@@ -4,6 +4,7 @@
 #pragma once
 #include "ctc_combine.cuh"
 #include "ctc_fused.cuh"
+#include "ctc_warp.cuh"
 
 namespace ctcb200 {
 
@@ -11,11 +12,12 @@ struct Variant {
     int NS, W, K, VCH;
     void (*kernel)(const FusedParams);
     void (*combine)(const CombineParams);      // latency ladder only: second half of the bidirectional path
+    int warp;                                  // 1: ctc_warp_kernel (persistent, one warp per utterance; ctc_warp.cuh)
     int max_label() const { return (32 * NS * W) / 2 - 1; }   // SP = 32*NS*W states must hold 2L+2
     int sp() const { return 32 * NS * W; }
 };
 
-enum Ladder { LADDER_THROUGHPUT = 0, LADDER_THROUGHPUT_K8 = 1, LADDER_LATENCY = 2, NUM_LADDERS = 3 };
+enum Ladder { LADDER_THROUGHPUT = 0, LADDER_THROUGHPUT_K8 = 1, LADDER_LATENCY = 2, LADDER_WARP = 3, NUM_LADDERS = 4 };
 constexpr int kMaxVch = 2;                     // alphabets up to 64 symbols (reference: 29 and 43)
 
 // group id = ladder * kMaxVch + (VCH - 1)
@@ -25,5 +27,7 @@ const Variant *ctc_variants_group2(int *n);
 const Variant *ctc_variants_group3(int *n);
 const Variant *ctc_variants_group4(int *n);
 const Variant *ctc_variants_group5(int *n);
+const Variant *ctc_variants_group6(int *n);
+const Variant *ctc_variants_group7(int *n);
 
 }  // namespace ctcb200
