@@ -26,12 +26,17 @@
 //    the two-sided test |Q_c / Z^ - 1| <= tol at all chunk starts bounds the posterior error of every frame.
 //  * Checkpoints are 32-bit (rounded high words), the softmax image is the r row itself (4*32 bytes per frame and
 //    32-symbol slice): extra HBM traffic per frame 4*NS*32/K*2 + 2*128 bytes.
+//  * An utterance is cut into T / K full chunks of K frames and T % K tail chunks of ONE frame; the chunk bodies
+//    are instantiated for both lengths and fully unrolled, so there is no per-frame "is this frame valid" test
+//    (those tests and the divergence checks ptxas wraps around them were 15 % of the first version's instructions).
 //  * Persistent CTAs: the grid is sized to the resident warps and pulls utterances (longest first) from an
 //    atomic queue, so the workspace is per resident CTA, not per utterance.
 //
 // Thread/state map: lane owns states s = lane*NS + i, i < NS (NS even => even i are blanks).
 // tests/proto_ratio.py models exactly this arithmetic on the CPU (<= 1.2e-6 max |dgrad| against the float64 oracle).
 #pragma once
+#include <type_traits>
+
 #include "ctc_fused.cuh"
 
 namespace ctcb200 {
@@ -60,14 +65,22 @@ __host__ __device__ inline WarpLayout make_warp_layout(int NS, int K, int VCH)
     return l;
 }
 
-// words (4 bytes) of workspace per resident CTA: checkpoint columns, r images, 1/s + chunk exponent
+// chunks of an utterance of T frames: T / K full chunks of K frames, then T % K tail chunks of one frame
+__host__ __device__ inline int warp_max_chunks(int K, int T_max) { return T_max / K + (K - 1); }
+
+// words (4 bytes) of workspace per resident CTA: checkpoint columns + exponent per chunk, r image + 1/s per frame
 __host__ __device__ inline long long warp_slot_words(int NS, int K, int VCH, int T_max)
 {
-    const long long nC = (T_max + K - 1) / K;
-    return nC * (32LL * NS + 32LL * K * VCH + (K + 1));
+    const long long nC = warp_max_chunks(K, T_max);
+    return nC * (32LL * NS + 1) + (long long)T_max * (32LL * VCH + 1);
 }
 
 __device__ __forceinline__ double hi2d(unsigned hi) { return __hiloint2double((int)hi, 0); }
+
+__device__ __forceinline__ float hi2f(unsigned hi)          // float of a (non-poisoned) ratio high word; below the
+{                                                           // float range: (sub)normal garbage <= 2^-126, i.e. 0
+    return __int_as_float(__viaddmax_s32((int)hi, -0x38000000, 0) << 3);
+}
 
 // r = exp(d) as the high word of a double (20 mantissa bits, truncated) and as the float of that truncated value.
 // d < -700: exactly 0.  d > 69 or NaN: poisoned (the utterance is flagged and redone in log space) -- 2^100 per
@@ -88,15 +101,8 @@ __device__ __forceinline__ unsigned ratio_hi(float d, float &rf)
     const bool pois = !(d <= 69.f);
     hi = tiny ? 0u : hi;
     hi = pois ? 0x7ff80000u : hi;
-    const unsigned fb = (hi - 0x38000000u) << 3;            // float bits when the exponent is inside the float range
-    rf = __uint_as_float(hi >= 0x38100000u ? fb : 0u);
-    rf = pois ? __int_as_float(0x7fc00000) : rf;
+    rf = pois ? __int_as_float(0x7fc00000) : hi2f(hi);
     return hi;
-}
-__device__ __forceinline__ float hi2f(unsigned hi)          // float of a (non-poisoned) ratio high word
-{
-    const unsigned fb = (hi - 0x38000000u) << 3;
-    return __uint_as_float((hi >= 0x38100000u && hi < 0x47f00000u) ? fb : (hi >= 0x47f00000u ? 0x7fc00000u : 0u));
 }
 __device__ __forceinline__ unsigned hi_round(double x)      // high word, rounded to nearest
 {
@@ -177,10 +183,20 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
     int *off_s = (int *)(smem + lay.off_off);
     const long long gst = (long long)P.B * V;               // gradient row stride (dense)
     const bool want_grad = (P.grads != nullptr);
-    const int nCmax = (P.T_max + K - 1) / K;
+    const int nCmax = warp_max_chunks(K, P.T_max);
     unsigned *ckw = (unsigned *)P.ckpt + (long long)blockIdx.x * (P.ckpt_stride * 2);   // [nCmax][NS][32] checkpoint high words
-    unsigned *imgw = ckw + (long long)nCmax * SP;                                   // [nCmax][K][VCH][32] r high words
-    float *invw = (float *)(imgw + (long long)nCmax * K * VCH * 32);                // [nCmax][K+1]: 1/s per frame, Ea of the chunk
+    int *eaw = (int *)(ckw + (long long)nCmax * SP);                                // [nCmax] alpha exponent of the chunk
+    unsigned *imgw = (unsigned *)(eaw + nCmax);                                     // [T_max][VCH][32] r high words
+    float *invw = (float *)(imgw + (long long)P.T_max * VCH * 32);                  // [T_max] 1 / s_t
+    const int bl = blank & 31, bs = blank >> 5;
+    const double m_first = (lane == 0) ? 0.0 : 1.0;         // lane 0 has no lower neighbour, lane 31 no upper one:
+    const double m_last = (lane == 31) ? 0.0 : 1.0;         //   folded into an fma instead of a select per step
+    bool colok[VCH], wr[VCH];
+#pragma unroll
+    for (int v = 0; v < VCH; ++v) {
+        colok[v] = (lane + 32 * v < V);
+        wr[v] = colok[v] && (lane + 32 * v != blank);
+    }
 
     for (int round = 0;; ++round) {
         int item;
@@ -301,19 +317,17 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         }
         __syncwarp();
 
-        const int nC = (T + K - 1) / K;
-        const int bl = blank & 31, bs = blank >> 5;
+        const int nfull = T / K, ntail = T - nfull * K;
 
-        // Raw activations of a chunk: lane = symbol, rows loaded one chunk ahead of their use (registers).
+        // Raw activations: lane = symbol; the rows of a full chunk are loaded one chunk ahead of their use.
         float xr[K][VCH];
-        auto issue_loads = [&](int c) {
-            const int t0 = c * K;
+        auto load_rows = [&](auto tag, int t0) {
+            constexpr int KK = decltype(tag)::value;
             const float *src = acts_b + (long long)t0 * P.act_stride_t + lane;
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt) {
+            for (int tt = 0; tt < KK; ++tt) {
 #pragma unroll
-                for (int v = 0; v < VCH; ++v)
-                    xr[tt][v] = (t0 + tt < T && lane + 32 * v < V) ? __ldg(src + 32 * v) : -INFINITY;
+                for (int v = 0; v < VCH; ++v) xr[tt][v] = colok[v] ? __ldg(src + 32 * v) : 0.f;
                 src += P.act_stride_t;
             }
         };
@@ -328,17 +342,16 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         };
         // one alpha step in place (descending i keeps the old neighbours intact)
         auto alpha_step = [&](double (&a)[NS], const unsigned (&row)[VCH]) {
-            double up1 = shfl_up_d(a[NS - 1]);
-            if (lane == 0) up1 = 0.0;
+            const double up1 = shfl_up_d(a[NS - 1]);
 #pragma unroll
             for (int i = NS - 1; i >= 0; --i) {
                 if (i & 1) {
                     const int jj = i >> 1;
                     const double pl = hi2d(lookup(row, lsrc[jj]));
-                    const double p2 = (i >= 2) ? a[i - 2] : up1;
+                    const double p2 = (i >= 2) ? a[i - 2] : up1;           // (i == 1: msk[0] is 0 on lane 0)
                     a[i] = fma(msk[jj], p2, a[i] + a[i - 1]) * pl;
                 } else {
-                    a[i] = a[i] + ((i >= 1) ? a[i - 1] : up1);
+                    a[i] = (i >= 1) ? a[i] + a[i - 1] : fma(m_first, up1, a[i]);
                 }
             }
         };
@@ -353,12 +366,12 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         unsigned hmax = 0u;                                 // largest ratio high word seen (poison detector)
         unsigned rcur[K][VCH];
 
-        issue_loads(0);
-        for (int c = 0; c < nC; ++c) {
-            const int n = min(K, T - c * K);
+        // forward chunk of KK frames starting at t0 (rows already in xr); checkpoint index ci
+        auto fwd_chunk = [&](auto tag, int t0, int ci, int t0_next) {
+            constexpr int KK = decltype(tag)::value;
             {   // states below S - 2(T - t) can no longer reach the end of the transcript: zero them (exact), which
                 // also keeps them out of the column max (see ctc_fused.cuh)
-                const int lo = S - 2 * (T - c * K + 1);
+                const int lo = S - 2 * (T - t0 + 1);
                 if (lo > 0) {
 #pragma unroll
                     for (int i = 0; i < NS; ++i) if (lane * NS + i < lo) a[i] = 0.0;
@@ -366,46 +379,48 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             }
             warp_rescale<NS>(a, Ea);
             if (want_grad) {
+                unsigned *cp = ckw + (long long)ci * SP + lane;
 #pragma unroll
-                for (int i = 0; i < NS; ++i) ckw[((long long)c * NS + i) * 32 + lane] = hi_round(a[i]);
+                for (int i = 0; i < NS; ++i) cp[i * 32] = hi_round(a[i]);
+                if (lane == 0) eaw[ci] = Ea;
             }
-            // ratios of the chunk's rows; lane tt keeps s_tt
-            float mys = 1.f;
+            // ratios of the chunk's rows; lane tt ends up with s_tt
+            float sv[KK];
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt) {
-                if (tt >= n) break;
+            for (int tt = 0; tt < KK; ++tt) {
                 const float xb = __shfl_sync(kFull, (VCH == 2 && bs) ? xr[tt][VCH - 1] : xr[tt][0], bl);
-                float s = 0.f;
+                sv[tt] = 0.f;
 #pragma unroll
                 for (int v = 0; v < VCH; ++v) {
                     float rf;
-                    unsigned h = ratio_hi(xr[tt][v] - xb, rf);
-                    if (lane + 32 * v >= V) { h = 0u; rf = 0.f; }
+                    const unsigned h = ratio_hi((colok[v] ? xr[tt][v] : -INFINITY) - xb, rf);
                     rcur[tt][v] = h;
                     hmax = max(hmax, h);
-                    s += rf;
+                    sv[tt] += rf;
                 }
-                s = warp_sum_f(s);
-                mys = (lane == tt) ? s : mys;
             }
-            if (c + 1 < nC) issue_loads(c + 1);
+            if (t0_next >= 0) load_rows(std::integral_constant<int, K>(), t0_next);
+            const float mys = warp_sum_transposed<KK>(sv, lane);
             const float myinv = 1.f / mys;
-            if (lane < n) lsum += (double)CTC_ROW_LOG(mys);
+            if (lane < KK) lsum += (double)CTC_ROW_LOG(mys);
             if (want_grad) {
+                unsigned *ip = imgw + (long long)t0 * (VCH * 32) + lane;
 #pragma unroll
-                for (int tt = 0; tt < K; ++tt) {
-                    if (tt >= n) break;
+                for (int tt = 0; tt < KK; ++tt)
 #pragma unroll
-                    for (int v = 0; v < VCH; ++v)
-                        imgw[(((long long)c * K + tt) * VCH + v) * 32 + lane] = rcur[tt][v];
-                }
-                if (lane <= K) invw[(long long)c * (K + 1) + lane] = (lane < K) ? myinv : __int_as_float(Ea);
+                    for (int v = 0; v < VCH; ++v) ip[(tt * VCH + v) * 32] = rcur[tt][v];
+                if (lane < KK) invw[t0 + lane] = myinv;
             }
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt) {
-                if (tt >= n) break;
-                alpha_step(a, rcur[tt]);
-            }
+            for (int tt = 0; tt < KK; ++tt) alpha_step(a, rcur[tt]);
+        };
+
+        if (nfull > 0) load_rows(std::integral_constant<int, K>(), 0);
+        for (int c = 0; c < nfull; ++c)
+            fwd_chunk(std::integral_constant<int, K>(), c * K, c, (c + 1 < nfull) ? (c + 1) * K : -1);
+        for (int u = 0; u < ntail; ++u) {
+            load_rows(std::integral_constant<int, 1>(), nfull * K + u);
+            fwd_chunk(std::integral_constant<int, 1>(), nfull * K + u, nfull + u, -1);
         }
 
         // Z^ = alpha^_{T-1}(S-1) + alpha^_{T-1}(S-2)
@@ -468,79 +483,74 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         int Eb = -kWarpTargetExp;
         float chk_dev = 0.f;
 
+        // operands of a backward chunk, loaded by the same lanes that wrote them (plain program order)
         unsigned cknext[NS], rnext[K][VCH];
         float invnext = 0.f;
-        auto prefetch = [&](int c) {
+        int eanext = 0;
+        auto prefetch = [&](auto tag, int t0, int ci) {
+            constexpr int KK = decltype(tag)::value;
+            const unsigned *cp = ckw + (long long)ci * SP + lane;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) cknext[i] = __ldcg(ckw + ((long long)c * NS + i) * 32 + lane);
+            for (int i = 0; i < NS; ++i) cknext[i] = __ldcg(cp + i * 32);
+            const unsigned *ip = imgw + (long long)t0 * (VCH * 32) + lane;
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt)
+            for (int tt = 0; tt < KK; ++tt)
 #pragma unroll
-                for (int v = 0; v < VCH; ++v)
-                    rnext[tt][v] = __ldcg(imgw + (((long long)c * K + tt) * VCH + v) * 32 + lane);
-            if (lane <= K) invnext = __ldcg(invw + (long long)c * (K + 1) + lane);
+                for (int v = 0; v < VCH; ++v) rnext[tt][v] = __ldcg(ip + (tt * VCH + v) * 32);
+            if (lane < KK) invnext = __ldcg(invw + t0 + lane);
+            eanext = __ldcg(eaw + ci);
         };
-        __syncwarp();
-        __threadfence_block();
-        prefetch(nC - 1);
 
-        for (int c = nC - 1; c >= 0; --c) {
-            const int t0 = c * K, n = min(K, T - t0);
+        // backward chunk of KK frames starting at t0: operands are in cknext / rnext / invnext / eanext
+        auto bwd_chunk = [&](auto tag, int t0, int t0_prev, int ci_prev) {
+            constexpr int KK = decltype(tag)::value;
 #pragma unroll
             for (int i = 0; i < NS; ++i) a[i] = hi2d(cknext[i]);
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt)
+            for (int tt = 0; tt < KK; ++tt)
 #pragma unroll
                 for (int v = 0; v < VCH; ++v) rcur[tt][v] = rnext[tt][v];
             const float myinv = invnext;
-            const int Ea_c = __shfl_sync(kFull, __float_as_int(invnext), K);
-            if (c >= 1) prefetch(c - 1);
-            int esc = Ea_c + Eb - Ea_fin - ez;
+            int esc = eanext + Eb - Ea_fin - ez;
+            if (t0_prev >= 0) prefetch(std::integral_constant<int, K>(), t0_prev, ci_prev);
             esc = max(-1000, min(esc, 700));
             const int esc_hi = esc * (1 << 20);
 
             // -- recompute alpha inside the chunk from its checkpoint; keep the label states (scaled high words) --
-            int av[K][NL];
+            int av[KK][NL];
             int ab[NL];                                     // blank states of the first frame (range check)
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt) {
-                if (tt < n) {
-                    alpha_step(a, rcur[tt]);
+            for (int tt = 0; tt < KK; ++tt) {
+                alpha_step(a, rcur[tt]);
 #pragma unroll
-                    for (int jj = 0; jj < NL; ++jj) av[tt][jj] = max(__double2hiint(a[2 * jj + 1]) + esc_hi, 0);
-                    if (tt == 0) {
+                for (int jj = 0; jj < NL; ++jj) av[tt][jj] = __viaddmax_s32(__double2hiint(a[2 * jj + 1]), esc_hi, 0);
+                if (tt == 0) {
 #pragma unroll
-                        for (int jj = 0; jj < NL; ++jj) ab[jj] = max(__double2hiint(a[2 * jj]) + esc_hi, 0);
-                    }
-                } else {
-#pragma unroll
-                    for (int jj = 0; jj < NL; ++jj) av[tt][jj] = 0;
+                    for (int jj = 0; jj < NL; ++jj) ab[jj] = __viaddmax_s32(__double2hiint(a[2 * jj]), esc_hi, 0);
                 }
             }
 
             // -- beta over the chunk; products alpha * tb go to shared memory grouped by symbol --
             double q = 0.0;
 #pragma unroll
-            for (int tt = K - 1; tt >= 0; --tt) {
-                if (tt < n) {
-                    double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);
-                    if (lane == 31) { dn0 = 0.0; dn1 = 0.0; }
+            for (int tt = KK - 1; tt >= 0; --tt) {
+                const double dn0 = shfl_down_d(bt[0]), dn1 = shfl_down_d(bt[1]);
+                float *prow = prod + tt * PS;
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) {
-                        if (i & 1) {
-                            const int jj = i >> 1;
-                            const double pl = hi2d(lookup(rcur[tt], lsrc[jj]));
-                            const double n1 = (i + 1 < NS) ? bt[i + 1] : dn0;
-                            const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;
-                            const double tb = fma(msk[jj + 1], n2, bt[i] + n1);
-                            const double pr = hi2d((unsigned)av[tt][jj]) * tb;
-                            if (tt == 0) q += pr;
-                            prod[tt * PS + sl[jj]] = (float)pr;
-                            bt[i] = tb * pl;
-                        } else {
-                            bt[i] = bt[i] + bt[i + 1];
-                            if (tt == 0) q = fma(hi2d((unsigned)ab[i >> 1]), bt[i], q);
-                        }
+                for (int i = 0; i < NS; ++i) {
+                    if (i & 1) {
+                        const int jj = i >> 1;
+                        const double pl = hi2d(lookup(rcur[tt], lsrc[jj]));
+                        const double s1 = (i + 1 < NS) ? bt[i] + bt[i + 1] : fma(m_last, dn0, bt[i]);
+                        const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;  // (msk[NL] is 0 on lane 31)
+                        const double tb = fma(msk[jj + 1], n2, s1);
+                        const double pr = hi2d((unsigned)av[tt][jj]) * tb;
+                        if (tt == 0) q += pr;
+                        prow[sl[jj]] = (float)pr;
+                        bt[i] = tb * pl;
+                    } else {
+                        bt[i] = bt[i] + bt[i + 1];
+                        if (tt == 0) q = fma(hi2d((unsigned)ab[i >> 1]), bt[i], q);
                     }
                 }
             }
@@ -552,44 +562,42 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                 chk_dev = fmaxf(chk_dev, (dev == dev) ? fabsf(dev) : INFINITY);
             }
 
-            // -- gather: lane k sums the products of symbol k for the K frames of the chunk --
-            float tot[K];
-            float post[VCH][K];
+            // -- gather: lane k sums the products of symbol k for the KK frames of the chunk --
+            float tot[KK];
+            float post[VCH][KK];
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt) tot[tt] = 0.f;
+            for (int tt = 0; tt < KK; ++tt) tot[tt] = 0.f;
 #pragma unroll
             for (int v = 0; v < VCH; ++v) {
-                float acc[K];
+                float acc[KK];
 #pragma unroll
-                for (int tt = 0; tt < K; ++tt) acc[tt] = 0.f;
+                for (int tt = 0; tt < KK; ++tt) acc[tt] = 0.f;
                 const float *gp = prod + koff[v];
                 for (int qq = 0; qq < kcnt[v]; ++qq) {
 #pragma unroll
-                    for (int tt = 0; tt < K; ++tt) acc[tt] += gp[tt * PS + qq];
+                    for (int tt = 0; tt < KK; ++tt) acc[tt] += gp[tt * PS + qq];
                 }
 #pragma unroll
-                for (int tt = 0; tt < K; ++tt) {
+                for (int tt = 0; tt < KK; ++tt) {
                     post[v][tt] = acc[tt] * inv_zm;
                     tot[tt] += post[v][tt];
                 }
             }
-            const float total = warp_sum_transposed<K>(tot, lane);      // lane l: sum over symbols of frame l & (K-1)
-            // gradient rows: lane = symbol (coalesced), the blank entry of frame tt is written by lane tt
+            // gradient rows: lane = symbol (coalesced); the blank entry of frame tt is written by lane tt
+            float *grow = grads_b + (long long)t0 * gst + lane;
 #pragma unroll
-            for (int tt = 0; tt < K; ++tt) {
-                if (tt < n) {
-                    const float inv_t = __shfl_sync(kFull, myinv, tt);
-                    float *grow = grads_b + (long long)(t0 + tt) * gst;
+            for (int tt = 0; tt < KK; ++tt) {
+                const float inv_t = __shfl_sync(kFull, myinv, tt);
 #pragma unroll
-                    for (int v = 0; v < VCH; ++v) {
-                        const int k = lane + 32 * v;
-                        const float g = (hi2f(rcur[tt][v]) * inv_t - post[v][tt]) * P.grad_scale;
-                        if (k < V && k != blank) grow[k] = g;
-                    }
+                for (int v = 0; v < VCH; ++v) {
+                    const float g = (hi2f(rcur[tt][v]) * inv_t - post[v][tt]) * P.grad_scale;
+                    if (wr[v]) grow[32 * v] = g;
                 }
+                grow += gst;
             }
-            if (lane < n) {
-                const float g = (myinv - (one - total)) * P.grad_scale;     // p(blank) = 1 / s
+            const float total = warp_sum_transposed<KK>(tot, lane);     // lane l: sum over symbols of frame l & (KK-1)
+            if (lane < KK) {
+                const float g = (myinv - (one - total)) * P.grad_scale; // p(blank) = 1 / s
                 grads_b[(long long)(t0 + lane) * gst + blank] = g;
             }
             {   // bt holds column t0.  States above 2*t0 + 1 cannot be reached from the start: zero them
@@ -601,7 +609,15 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             }
             warp_rescale<NS>(bt, Eb);
             __syncwarp();                                   // gather reads done before the next chunk's products
+        };
+
+        for (int u = ntail - 1; u >= 0; --u) {
+            prefetch(std::integral_constant<int, 1>(), nfull * K + u, nfull + u);
+            bwd_chunk(std::integral_constant<int, 1>(), nfull * K + u, -1, 0);
         }
+        if (nfull > 0) prefetch(std::integral_constant<int, K>(), (nfull - 1) * K, nfull - 1);
+        for (int c = nfull - 1; c >= 0; --c)
+            bwd_chunk(std::integral_constant<int, K>(), c * K, (c >= 1) ? (c - 1) * K : -1, c - 1);
 
         if (!(chk_dev <= kCheckTol)) ustat |= UTT_RANGE;
         if (__any_sync(kFull, ustat & UTT_RANGE)) ustat |= UTT_RANGE;
