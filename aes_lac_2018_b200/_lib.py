@@ -56,6 +56,7 @@ class CtcB200Call(ctypes.Structure):
         ("flags", ctypes.c_uint),
         ("debug_device", ctypes.c_void_p),
         ("kernel_ms_host", ctypes.c_void_p),
+        ("status_device", ctypes.c_void_p),
     ]
 
 
@@ -85,7 +86,7 @@ class CtcB200HostCall(ctypes.Structure):
 EXPORTS = ("get_warpctc_version", "ctcGetStatusString", "compute_ctc_loss", "get_workspace_size",
            "ctc_b200_workspace_size", "ctc_b200_compute", "ctc_b200_last_error", "ctc_b200_info",
            "ctc_b200_workspace_size_host", "ctc_b200_compute_host", "ctc_b200_greedy_decode",
-           "ctc_b200_edit_distance", "ctc_b200_head_workspace_size", "ctc_b200_head_forward", "ctc_b200_head_backward")
+           "ctc_b200_edit_distance", "ctc_b200_reduce_costs", "ctc_b200_scale_gradients", "ctc_b200_head_workspace_size", "ctc_b200_head_forward", "ctc_b200_head_backward")
 
 class CtcB200HeadForward(ctypes.Structure):
     _fields_ = [("x", ctypes.c_void_p), ("rows", ctypes.c_int), ("features", ctypes.c_int), ("classes", ctypes.c_int),
@@ -159,6 +160,12 @@ def load() -> ctypes.CDLL:
     lib.ctc_b200_head_forward.argtypes = [ctypes.POINTER(CtcB200HeadForward)]
     lib.ctc_b200_head_backward.restype = ctypes.c_int
     lib.ctc_b200_head_backward.argtypes = [ctypes.POINTER(CtcB200HeadBackward)]
+    lib.ctc_b200_reduce_costs.restype = ctypes.c_int
+    lib.ctc_b200_reduce_costs.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+    lib.ctc_b200_scale_gradients.restype = ctypes.c_int
+    lib.ctc_b200_scale_gradients.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_float, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]
     lib.ctc_b200_compute.restype = ctypes.c_int
     lib.ctc_b200_compute.argtypes = [ctypes.POINTER(CtcB200Call)]
     _lib = lib

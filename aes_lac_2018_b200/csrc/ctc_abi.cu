@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,7 +38,8 @@ ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
 // SP = 32*NS*W padded states; an utterance with L labels fits when SP >= 2L + 2.
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kBidirMaxB = 96;              // bidirectional (two sweeps + combine) path for batches up to this size
+constexpr int kBidirMaxB = 96;              // bidirectional (two sweeps + combine) path for batches up to this size ...
+constexpr size_t kBidirMaxBytes = 192u << 20;   // ... and up to this many bytes of spilled columns
 constexpr int kWarpMinB = 2048;             // automatic ladder choice: warp ladder from this batch size
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
 constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)
@@ -126,13 +128,18 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     int t_min = 0x7fffffff, t_max = 0;
     // Small batches (bidirectional path): one variant for everybody -- the per-step latency of the latency ladder
     // barely depends on the variant, while every extra bucket costs two more launches and a stream fork/join.
-    const bool one_bucket = (mode == 2) && want_grad && B <= kBidirMaxB;
     cls_of_len.resize((size_t)max_L + 1);                // label length -> variant index, once per call
     for (int L = 0, c = 0; L <= max_L; ++L) {
         while (c < nl && ladder[c].max_label() < L) ++c;
         if (c >= nl) return fail(CTC_STATUS_UNKNOWN_ERROR, "no kernel variant for this label length");
         cls_of_len[L] = c;
     }
+    // The bidirectional path spills every column of two sweeps: 2 * B * T_max * SP * 4 bytes with SP taken from the
+    // LONGEST transcript (one bucket).  Long utterances would turn that into gigabytes of workspace next to the
+    // model (B = 96, T = 1500, L = 400: 1.2 GB), so it is only taken while it stays under a fixed budget; above it
+    // the checkpointed three-sweep kernel (no spill) runs instead.
+    const size_t bidir_spill = sizeof(unsigned) * 2 * (size_t)B * (size_t)T_max * (size_t)ladder[cls_of_len[max_L]].sp();
+    const bool one_bucket = (mode == 2) && want_grad && B <= kBidirMaxB && bidir_spill <= kBidirMaxBytes;
     for (int b = 0; b < B; ++b) {
         cls[b] = cls_of_len[one_bucket ? max_L : label_len[b]];
         ++count[cls[b]];
@@ -163,10 +170,10 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     plan.off_labels = o; o = align_up(o + sizeof(int) * (size_t)std::max<long long>(off, 1), 256);
     plan.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
     plan.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
-    plan.off_queue = o;  o = align_up(o + sizeof(int) * kMaxLaunches, 256);
+    plan.off_queue = o;  o = align_up(o + sizeof(int) * (kMaxLaunches + 1), 256);   // (+1: the log-space detour)
     plan.off_ckpt = o;
     size_t ck = 0, bd = 0;
-    plan.bidir = plan.latency && want_grad && B <= kBidirMaxB;
+    plan.bidir = one_bucket;
     for (int c = nl - 1; c >= 0; --c) {                  // launch order: descending variant index
         if (count[c] == 0) continue;
         const Variant *v = &ladder[c];
@@ -188,7 +195,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         l.col_off = bd;  bd = align_up(bd + sizeof(unsigned) * 2 * (size_t)l.count * (size_t)T_max * v->sp(), 256);
         l.exp_off = bd;  bd = align_up(bd + sizeof(int) * 2 * (size_t)l.count * l.exp_stride, 256);
         l.z_off = bd;    bd = align_up(bd + sizeof(double) * 2 * (size_t)l.count * 4, 256);
-        l.smem = v->warp ? make_warp_layout(v->NS, v->K, v->VCH).total : make_layout(v->NS, v->W, v->K, V, T_max).total;
+        l.smem = v->warp ? make_warp_layout(v->NS, v->K, v->VCH, v->warp == 2).total : make_layout(v->NS, v->W, v->K, V, T_max).total;
         if (l.smem > kMaxSmem)
             return fail(CTC_STATUS_UNKNOWN_ERROR,
                         "alphabet_size / max_time too large for the shared-memory layout of this kernel");
@@ -281,45 +288,37 @@ int persistent_grid(const void *kernel, int smem)
     return grid;
 }
 
-constexpr unsigned kFlagForceLogspace = 0x80000000u;    // internal: skip the fused kernels, log-space for every utterance
-
-// Re-run the listed utterances with the fp64 log-space kernel (ctc_logspace.cuh).  The fused kernels of this
-// call have completed (the caller synchronised), so their checkpoint area is free: it is cut into alpha slots
-// of 8*T_max*S_max bytes and the utterances are processed in rounds of as many slots as fit.
-ctcStatus_t run_logspace_fallback(const ctcB200Call &c, const Plan &plan, const FusedParams &FP,
-                                  const std::vector<int> &todo, cudaStream_t stream)
+// Enqueue the device-side log-space detour behind the fast kernels of this call (ctc_logspace.cuh): persistent CTAs
+// scan the status words and redo the utterances flagged RANGE / INF_COST in fp64 log space.  The fast kernels have
+// been ordered before it on `stream`, so their checkpoint area is free: it is cut into alpha slots of
+// 8 * T_max * S_max bytes, one per CTA.
+ctcStatus_t launch_logspace_detour(const ctcB200Call &c, const Plan &plan, const FusedParams &FP, int *d_queue,
+                                   cudaStream_t stream)
 {
     ctcStatus_t st = CTC_STATUS_SUCCESS;
     const int B = c.minibatch, V = c.alphabet_size;
     char *ws = (char *)c.workspace;
-    int S_max = 1;
-    for (int b : todo) S_max = std::max(S_max, 2 * c.label_lengths[b] + 1);
+    const int S_max = plan.fallback_S;
     const size_t slot_doubles = (size_t)c.max_time * (size_t)S_max;
-    const size_t n_slots = std::min<size_t>(todo.size(), plan.ckpt_bytes / (slot_doubles * sizeof(double)));
-    if (n_slots == 0) return fail(CTC_STATUS_EXECUTION_FAILED, "workspace too small for the log-space fallback");
+    const size_t n_slots = plan.ckpt_bytes / (slot_doubles * sizeof(double));
+    if (n_slots == 0) return fail(CTC_STATUS_EXECUTION_FAILED, "workspace too small for the log-space detour");
     const int smem = logspace_smem_bytes(S_max, V);
-    if (smem > kMaxSmem) return fail(CTC_STATUS_UNKNOWN_ERROR, "label sequence too long for the log-space fallback");
-    if (!check(cudaFuncSetAttribute(ctc_logspace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
-               "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-    int *d_list = (int *)(ws + plan.off_meta) + 3 * B;          // the utt_ids area is free again
-    if (!check(cudaMemcpyAsync(d_list, todo.data(), sizeof(int) * todo.size(), cudaMemcpyHostToDevice, stream),
-               "H2D fallback list", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+    if (smem > kMaxSmem) return fail(CTC_STATUS_UNKNOWN_ERROR, "label sequence too long for the log-space detour");
+    if (!ensure_smem_attr((const void *)ctc_logspace_kernel, smem, st)) return st;
     LogParams L;
     L.acts = FP.acts; L.act_stride_t = FP.act_stride_t; L.act_stride_b = FP.act_stride_b;
     L.grads = FP.grads;
     L.labels = FP.labels; L.label_off = FP.label_off; L.label_len = FP.label_len; L.act_len = FP.act_len;
+    L.queue = d_queue; L.n_utts = B;
     L.costs = FP.costs; L.status = FP.status;
     L.alpha_ws = (double *)(ws + plan.off_ckpt);
     L.slot_stride = (long long)slot_doubles;
     L.V = V; L.T_max = c.max_time; L.B = B; L.blank = c.blank_label; L.S_max = S_max;
     L.grad_scale = c.grad_scale;
-    for (size_t done = 0; done < todo.size(); done += n_slots) {
-        const int n = (int)std::min(n_slots, todo.size() - done);
-        L.utt_list = d_list + done;
-        ctc_logspace_kernel<<<n, kLogThreads, smem, stream>>>(L);
-        ++g_launches;
-        if (!check(cudaGetLastError(), "fallback launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-    }
+    const int grid = (int)std::min<size_t>(std::min<size_t>(n_slots, 296), (size_t)B);
+    ctc_logspace_kernel<<<grid, kLogThreads, smem, stream>>>(L);
+    ++g_launches;
+    if (!check(cudaGetLastError(), "log-space detour launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     return CTC_STATUS_SUCCESS;
 }
 
@@ -331,6 +330,7 @@ ctcStatus_t run(const ctcB200Call &c)
         return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
     if (c.blank_label < 0 || c.blank_label >= c.alphabet_size)
         return fail(CTC_STATUS_INVALID_VALUE, "blank_label outside the alphabet");
+    if (c.flags & ~0x70fu) return fail(CTC_STATUS_INVALID_VALUE, "unknown bits in flags");
     const bool no_sync = (c.flags & CTC_B200_FLAG_NO_SYNC) != 0;
     if (no_sync && (c.costs_host || c.status_host))
         return fail(CTC_STATUS_INVALID_VALUE, "NO_SYNC cannot return host costs/status");
@@ -350,7 +350,8 @@ ctcStatus_t run(const ctcB200Call &c)
     int *d_meta = (int *)(ws + plan.off_meta);
     int *d_labels = (int *)(ws + plan.off_labels);
     float *d_costs = c.costs_device ? c.costs_device : (float *)(ws + plan.off_costs);
-    int *d_status = g_status_dev_override ? g_status_dev_override : (int *)(ws + plan.off_status);
+    int *d_status = g_status_dev_override ? g_status_dev_override
+                    : (c.status_device ? c.status_device : (int *)(ws + plan.off_status));
 
     if (!check(cudaMemcpyAsync(d_meta, plan.meta.data(), sizeof(int) * 4 * (size_t)B, cudaMemcpyHostToDevice, stream),
                "H2D metadata", CTC_STATUS_MEMOPS_FAILED, st)) return st;
@@ -369,8 +370,7 @@ ctcStatus_t run(const ctcB200Call &c)
     P.queue = nullptr; P.n_items = 0;
     int *d_queue = (int *)(ws + plan.off_queue);
     if ((int)plan.launches.size() > kMaxLaunches) return fail(CTC_STATUS_UNKNOWN_ERROR, "too many kernel variants in one call");
-    if (!plan.launches.empty() && plan.launches[0].v->warp &&
-        !check(cudaMemsetAsync(d_queue, 0, sizeof(int) * kMaxLaunches, stream), "queue memset", CTC_STATUS_MEMOPS_FAILED, st))
+    if (!check(cudaMemsetAsync(d_queue, 0, sizeof(int) * (kMaxLaunches + 1), stream), "queue memset", CTC_STATUS_MEMOPS_FAILED, st))
         return st;
 
     const bool serial = (c.flags & CTC_B200_FLAG_SERIAL_LAUNCHES) != 0;
@@ -378,13 +378,11 @@ ctcStatus_t run(const ctcB200Call &c)
     if (tim && !check(cudaEventRecord(tim->t0, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     AuxStreams *aux = (plan.launches.size() > 1 && !serial) ? aux_streams() : nullptr;
     if (aux && !check(cudaEventRecord(aux->fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-    const bool force_log = (c.flags & kFlagForceLogspace) != 0;
-    const bool bidir = plan.bidir && want_grad && !force_log && !(c.flags & CTC_B200_FLAG_NO_BIDIR);
+    const bool bidir = plan.bidir && want_grad && !(c.flags & CTC_B200_FLAG_NO_BIDIR);
     P.sweep_only = 0; P.n_fwd = 0; P.col = nullptr; P.col_stride = 0; P.col_exp = nullptr; P.col_exp_stride = 0;
     P.col_z = nullptr;
     int n_aux_used = 0, li = 0;
     for (const Plan::Launch &l : plan.launches) {
-        if (force_log) break;
         P.utt_ids = d_meta + 3 * B + l.first;
         P.ckpt = (double *)(ws + plan.off_ckpt + l.ckpt_off);
         P.ckpt_stride = l.ckpt_stride;
@@ -437,10 +435,18 @@ ctcStatus_t run(const ctcB200Call &c)
         if (!check(cudaEventRecord(aux->join[j], aux->s[j]), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
         if (!check(cudaStreamWaitEvent(stream, aux->join[j], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     }
+    // Out-of-range utterances (Z^ underflowed to 0, the forward/backward consistency check failed, or a genuine +inf
+    // cost) are redone in log space by a kernel that finds them itself: no host round trip, so NO_SYNC calls get
+    // the detour too.
+    if (!(c.flags & CTC_B200_FLAG_NO_FALLBACK)) {
+        st = launch_logspace_detour(c, plan, P, d_queue + kMaxLaunches, stream);
+        if (st != CTC_STATUS_SUCCESS) return st;
+    }
     if (tim && !check(cudaEventRecord(tim->t1, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     if (no_sync) return CTC_STATUS_SUCCESS;
 
-    std::vector<int> h_status(B);
+    thread_local std::vector<int> h_status;
+    h_status.resize(B);
     if (c.costs_host &&
         !check(cudaMemcpyAsync(c.costs_host, d_costs, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, stream),
                "D2H costs", CTC_STATUS_MEMOPS_FAILED, st)) return st;
@@ -451,35 +457,14 @@ ctcStatus_t run(const ctcB200Call &c)
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, tim->t0, tim->t1) == cudaSuccess) *c.kernel_ms_host = ms;
     }
-
-    // Utterances whose column spread exceeded the fp64 range (Z^ underflowed to 0, or the forward/backward
-    // consistency check failed) are redone in log space; a genuine +inf cost simply comes back as +inf.
-    std::vector<int> todo;
-    for (int b = 0; b < B; ++b) {
-        if (force_log) { h_status[b] = 0; todo.push_back(b); }
-        else if ((h_status[b] & (CTC_B200_UTT_RANGE | CTC_B200_UTT_INF_COST)) && !(h_status[b] & CTC_B200_UTT_BAD_LABEL))
-            todo.push_back(b);
-    }
-    if (!todo.empty() && !(c.flags & CTC_B200_FLAG_NO_FALLBACK)) {
-        st = run_logspace_fallback(c, plan, P, todo, stream);
-        if (st != CTC_STATUS_SUCCESS) return st;
-        if (c.costs_host &&
-            !check(cudaMemcpyAsync(c.costs_host, d_costs, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, stream),
-                   "D2H costs", CTC_STATUS_MEMOPS_FAILED, st)) return st;
-        if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
-                   "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
-        if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-        for (int b : todo) h_status[b] |= CTC_B200_UTT_LOGSPACE;
-    }
     int any = 0;
     for (int b = 0; b < B; ++b) any |= h_status[b];
     if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
+    // Invalid ARGUMENTS are errors; hostile DATA is not: NaN activations (still CTC_B200_UTT_RANGE after the detour)
+    // come back as a NaN cost and NaN gradient rows with the status bit set -- what upstream does, and what lets the
+    // reference's trainer skip the step instead of dying (codes/engine.py:27-30).
     if (any & CTC_B200_UTT_BAD_LABEL)
         return fail(CTC_STATUS_INVALID_VALUE, "a label is outside [0, alphabet_size) or equals the blank");
-    if (any & CTC_B200_UTT_RANGE)
-        return fail(CTC_STATUS_EXECUTION_FAILED,
-                    (c.flags & CTC_B200_FLAG_NO_FALLBACK) ? "utterance outside the fp64 linear-domain range (fallback disabled)"
-                                                          : "non-finite partition function (NaN activations?)");
     return CTC_STATUS_SUCCESS;
 }
 
@@ -587,63 +572,55 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
     if (!check(cudaMemcpyAsync(h_status.data(), d_status, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, stream),
                "D2H status", CTC_STATUS_MEMOPS_FAILED, st)) return st;
     if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-    // Out-of-range utterances: gather them into a compact device batch and run the log-space kernel on it.
-    std::vector<int> todo;
-    for (int b = 0; b < B; ++b)
-        if ((h_status[b] & (CTC_B200_UTT_RANGE | CTC_B200_UTT_INF_COST)) && !(h_status[b] & CTC_B200_UTT_BAD_LABEL))
-            todo.push_back(b);
-    for (size_t done = 0; done < todo.size() && !(c.flags & CTC_B200_FLAG_NO_FALLBACK); done += (size_t)hp.Bc) {
-        const int n = (int)std::min<size_t>((size_t)hp.Bc, todo.size() - done);
-        char *base = ws + hp.off_sets;                      // buffer set 0 (all pipeline work has completed)
-        float *d_acts = (float *)base;
-        float *d_grads = want_grad ? (float *)(base + hp.acts_bytes) : nullptr;
-        void *inner = base + hp.acts_bytes * (want_grad ? 2 : 1);
-        std::vector<int> sub_ll(n), sub_al(n), sub_status(n);
-        std::vector<int> sub_labels;
-        std::vector<float> sub_costs(n);
-        std::vector<long long> offs(B + 1, 0);
-        for (int b = 0; b < B; ++b) offs[b + 1] = offs[b] + c.label_lengths[b];
-        for (int i = 0; i < n; ++i) {
-            const int b = todo[done + i];
-            sub_ll[i] = c.label_lengths[b]; sub_al[i] = c.input_lengths[b];
-            sub_labels.insert(sub_labels.end(), c.flat_labels + offs[b], c.flat_labels + offs[b + 1]);
-            if (!check(cudaMemcpy2DAsync(d_acts + (size_t)i * V, sizeof(float) * (size_t)n * V, c.activations + (size_t)b * V,
-                                         row_all, sizeof(float) * V, T, cudaMemcpyHostToDevice, stream),
-                       "H2D activations (fallback)", CTC_STATUS_MEMOPS_FAILED, st)) return st;
-        }
-        if (sub_labels.empty()) sub_labels.push_back(0);
-        ctcB200Call k;
-        std::memset(&k, 0, sizeof(k));
-        k.activations = d_acts; k.act_stride_t = (long long)n * V; k.act_stride_b = V;
-        k.gradients = d_grads;
-        k.flat_labels = sub_labels.data(); k.label_lengths = sub_ll.data(); k.input_lengths = sub_al.data();
-        k.alphabet_size = V; k.minibatch = n; k.max_time = T; k.blank_label = c.blank_label;
-        k.grad_scale = c.grad_scale;
-        k.costs_host = sub_costs.data(); k.status_host = sub_status.data();
-        k.workspace = inner; k.workspace_bytes = hp.inner_ws;
-        k.stream = (CUstream)stream;
-        k.flags = kFlagForceLogspace;
-        st = run(k);
-        if (st != CTC_STATUS_SUCCESS) return st;
-        for (int i = 0; i < n; ++i) {
-            const int b = todo[done + i];
-            c.costs_host[b] = sub_costs[i];
-            h_status[b] = sub_status[i];
-            if (want_grad &&
-                !check(cudaMemcpy2DAsync(c.gradients + (size_t)b * V, row_all, d_grads + (size_t)i * V, sizeof(float) * (size_t)n * V,
-                                         sizeof(float) * V, T, cudaMemcpyDeviceToHost, stream),
-                       "D2H gradients (fallback)", CTC_STATUS_MEMOPS_FAILED, st)) return st;
-        }
-        if (!check(cudaStreamSynchronize(stream), "stream sync", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-    }
+    // (out-of-range utterances were redone on the device by the detour kernel of their chunk's call)
     int any = 0;
     for (int b = 0; b < B; ++b) any |= h_status[b];
     if (c.status_host) std::memcpy(c.status_host, h_status.data(), sizeof(int) * (size_t)B);
     if (any & CTC_B200_UTT_BAD_LABEL)
         return fail(CTC_STATUS_INVALID_VALUE, "a label is outside [0, alphabet_size) or equals the blank");
-    if (any & CTC_B200_UTT_RANGE)
-        return fail(CTC_STATUS_EXECUTION_FAILED, "non-finite partition function (NaN activations?)");
     return CTC_STATUS_SUCCESS;
+}
+
+// ---- loss glue (include/ctc.h: ctc_b200_reduce_costs / ctc_b200_scale_gradients) ------------------
+constexpr int kReduceThreads = 1024;
+__global__ void __launch_bounds__(kReduceThreads) reduce_costs_kernel(const float *costs, int n, float scale, int zero_inf,
+                                                                       float *loss, int *flag)
+{
+    __shared__ double part[kReduceThreads / 32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += kReduceThreads) s += (double)costs[i];       // fixed assignment and order
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < kReduceThreads / 32; ++w) t += part[w];
+        t *= (double)scale;
+        const bool inf = (t == INFINITY) || (t == -INFINITY);
+        loss[0] = (inf && zero_inf) ? 0.f : (float)t;
+        if (flag) flag[0] = (inf && zero_inf) ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) scale_gradients_kernel(float4 *g4, float *g, size_t n4, size_t n, float scale_host,
+                                                               const float *scale_dev, const int *zero_flag)
+{
+    float f = scale_host * (scale_dev ? __ldg(scale_dev) : 1.f);
+    if (zero_flag && __ldg(zero_flag)) f = 0.f;
+    if (f == 1.f) return;                                   // the common case: no pass over the tensor
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if (f == 0.f) {                                         // (0 * inf and 0 * NaN must be 0 here: the step is being skipped)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] = 0.f;
+        return;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = g4[i];
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        g4[i] = v;
+    }
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) g[i] *= f;
 }
 
 }  // namespace
@@ -698,6 +675,35 @@ ctcStatus_t ctc_b200_compute(const ctcB200Call *call)
 {
     if (!call) return fail(CTC_STATUS_INVALID_VALUE, "null call");
     return run(*call);
+}
+
+ctcStatus_t ctc_b200_reduce_costs(const float *costs_device, int minibatch, float scale, int zero_infinite,
+                                  float *loss_device, int *flag_device, CUstream stream)
+{
+    if (!costs_device || !loss_device || minibatch <= 0) return fail(CTC_STATUS_INVALID_VALUE, "invalid argument");
+    reduce_costs_kernel<<<1, kReduceThreads, 0, (cudaStream_t)stream>>>(costs_device, minibatch, scale, zero_infinite,
+                                                                        loss_device, flag_device);
+    ++g_launches;
+    ctcStatus_t st = CTC_STATUS_SUCCESS;
+    if (!check(cudaGetLastError(), "reduce_costs launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    return CTC_STATUS_SUCCESS;
+}
+
+ctcStatus_t ctc_b200_scale_gradients(float *gradients, size_t count, float scale_host, const float *scale_device,
+                                     const int *zero_flag_device, CUstream stream)
+{
+    if (!gradients) return fail(CTC_STATUS_INVALID_VALUE, "null gradients");
+    if (count == 0) return CTC_STATUS_SUCCESS;
+    if (!scale_device && !zero_flag_device && scale_host == 1.f) return CTC_STATUS_SUCCESS;   // nothing to do, no launch
+    const bool aligned = (reinterpret_cast<uintptr_t>(gradients) & 15u) == 0;
+    const size_t n4 = aligned ? count / 4 : 0;
+    const int grid = (int)std::min<size_t>((std::max<size_t>(n4, 1) + 255) / 256, 148 * 8);
+    scale_gradients_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4 *>(gradients), gradients, n4,
+                                                                   count, scale_host, scale_device, zero_flag_device);
+    ++g_launches;
+    ctcStatus_t st = CTC_STATUS_SUCCESS;
+    if (!check(cudaGetLastError(), "scale_gradients launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    return CTC_STATUS_SUCCESS;
 }
 
 ctcStatus_t ctc_b200_workspace_size_host(const int *label_lengths, const int *input_lengths, int alphabet_size,

@@ -58,6 +58,7 @@ enum : int {
     UTT_INF_COST = 0x2,
     UTT_BAD_LABEL = 0x4,
     UTT_RANGE = 0x8,
+    UTT_LOGSPACE = 0x10,
 };
 
 struct FusedParams {

@@ -5,7 +5,10 @@
 // confident-and-wrong model (e.g. a blank-collapsed network asked for a long transcript: cost = L x margin,
 // thousands of nats) spreads a column over more than e^700 and the states that carry the result underflow.
 // The fast kernel detects this (Z^ = 0 -> CTC_B200_UTT_INF_COST, or its forward/backward consistency check
-// fails -> CTC_B200_UTT_RANGE); the host then re-runs exactly those utterances here.  Same maths as
+// fails -> CTC_B200_UTT_RANGE).  The detour is taken ON THE DEVICE: this kernel is enqueued right behind the fast
+// kernels of every call (same stream, no host round trip, so non-blocking calls get it too); its persistent CTAs
+// scan the status words of the batch and redo exactly the flagged utterances (none, almost always: the scan of
+// 8192 status words costs a few microseconds).  Same maths as
 // warp-ctc's compute_alpha_kernel / compute_betas_and_grad_kernel (log-space, beta includes the emission,
 // SURVEY.md Appendix C) but in float64 throughout, so it has no range limit and agrees with the oracle to
 // ~1e-12.  One CTA per utterance; alpha rows go to a caller-provided HBM slot (8*T*S bytes per utterance in
@@ -25,10 +28,11 @@ struct LogParams {
     long long act_stride_t, act_stride_b;
     float *grads;                     // dense [T_max][B][V] or nullptr
     const int *labels, *label_off, *label_len, *act_len;
-    const int *utt_list;              // [gridDim.x] utterances to redo
+    int *queue;                       // work counter over the batch (zeroed before the launch)
+    int n_utts;                       // utterances 0 .. n_utts-1 are scanned; those flagged RANGE / INF_COST are redone
     float *costs;
     int *status;
-    double *alpha_ws;                 // [gridDim.x] slots
+    double *alpha_ws;                 // [gridDim.x] slots (one per persistent CTA)
     long long slot_stride;            // doubles per slot (>= T_max * S_max)
     int V, T_max, B, blank, S_max;
     float grad_scale;
@@ -75,12 +79,11 @@ __device__ __forceinline__ double block_sum(double v, double *red, int tid)
     return s;
 }
 
-__global__ void __launch_bounds__(kLogThreads) ctc_logspace_kernel(const LogParams P)
+// one utterance, whole CTA; returns the CTC_B200_UTT_* bits of the result
+__device__ __forceinline__ int logspace_utterance(const LogParams &P, int b, unsigned char *smem)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, NT = kLogThreads;
     const int V = P.V, blank = P.blank;
-    const int b = P.utt_list[blockIdx.x];
     const int T = P.act_len[b], L = P.label_len[b], S = 2 * L + 1;
     const int SA = P.S_max + 2;
     double *prev = (double *)smem;                 // [SA]
@@ -165,11 +168,8 @@ __global__ void __launch_bounds__(kLogThreads) ctc_logspace_kernel(const LogPara
     int ustat = 0;
     if (logz == -INFINITY) ustat = UTT_INF_COST;
     else if (!(logz == logz)) ustat = UTT_RANGE;          // NaN activations
-    if (tid == 0) {
-        P.costs[b] = (float)(-logz);
-        P.status[b] = ustat;
-    }
-    if (!grads_b) return;
+    if (tid == 0) P.costs[b] = (float)(-logz);
+    if (!grads_b) return ustat;
 
     // ---------------- backward + gradient ----------------
     for (int t = T - 1; t >= 0; --t) {
@@ -215,6 +215,25 @@ __global__ void __launch_bounds__(kLogThreads) ctc_logspace_kernel(const LogPara
     }
     for (int t = T + (tid >> 5); t < P.T_max; t += NT / 32)
         for (int k = (tid & 31); k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
+    return ustat;
+}
+
+__global__ void __launch_bounds__(kLogThreads) ctc_logspace_kernel(const LogParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_item;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = atomicAdd(P.queue, 1);
+        __syncthreads();
+        const int b = s_item;
+        __syncthreads();
+        if (b >= P.n_utts) break;
+        const int st = P.status[b];
+        if (!(st & (UTT_RANGE | UTT_INF_COST)) || (st & UTT_BAD_LABEL)) continue;
+        const int ustat = logspace_utterance(P, b, smem);
+        __syncthreads();
+        if (threadIdx.x == 0) P.status[b] = ustat | UTT_LOGSPACE;
+    }
 }
 
 }  // namespace ctcb200

@@ -12,7 +12,8 @@ namespace ctcb200 {
 #if CTC_GROUP / 2 == 2
 #define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, ctc_combine_kernel<NS, W, K>, 0}
 #elif CTC_GROUP / 2 == 3
-#define VW_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp_kernel<NS, K, CTC_VCH, MAXR>, nullptr, 1}
+#define VW_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp_kernel<NS, K, CTC_VCH, MAXR, 0>, nullptr, 1}
+#define VWS_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp_kernel<NS, K, CTC_VCH, MAXR, 1>, nullptr, 2}
 #else
 #define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, nullptr, 0}
 #endif
@@ -31,7 +32,7 @@ static const Variant kTable[] = {
 #ifdef CTC_WARP_TABLE_INC          // kernel experiments: the table comes from a file (tools/build_alt.sh)
 #include CTC_WARP_TABLE_INC
 #else
-    VW_(2, 8, 128), VW_(4, 8, 128), VW_(6, 8, 128), VW_(8, 8, 168), VW_(10, 4, 168), VW_(12, 4, 168), VW_(14, 4, 168), VW_(16, 4, 168),
+    VW_(2, 8, 128), VW_(4, 8, 144), VW_(6, 8, 168), VW_(8, 8, 168), VW_(10, 4, 168), VW_(12, 4, 168), VW_(14, 4, 184), VW_(16, 4, 200),
 #endif
 #else
     // latency: more warps per utterance, fewer states per thread

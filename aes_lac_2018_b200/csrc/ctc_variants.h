@@ -12,7 +12,8 @@ struct Variant {
     int NS, W, K, VCH;
     void (*kernel)(const FusedParams);
     void (*combine)(const CombineParams);      // latency ladder only: second half of the bidirectional path
-    int warp;                                  // 1: ctc_warp_kernel (persistent, one warp per utterance; ctc_warp.cuh)
+    int warp;                                  // 1, 2: ctc_warp_kernel (persistent, one warp per utterance; ctc_warp.cuh);
+                                               // 2 = recomputed alpha staged in shared memory instead of registers
     int max_label() const { return (32 * NS * W) / 2 - 1; }   // SP = 32*NS*W states must hold 2L+2
     int sp() const { return 32 * NS * W; }
 };

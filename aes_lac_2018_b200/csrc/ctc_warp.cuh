@@ -46,10 +46,11 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct WarpLayout {
     int PS;                              // product row stride (floats); slot PS-1 is the dump slot of padding labels
-    int off_prod, off_lab, off_slot, off_cnt, off_off, total;
+    int off_prod, off_lab, off_slot, off_cnt, off_off, off_av, total;
 };
 
-__host__ __device__ inline WarpLayout make_warp_layout(int NS, int K, int VCH)
+// avs: the recomputed alpha of the label states waits for the beta steps in shared memory instead of registers
+__host__ __device__ inline WarpLayout make_warp_layout(int NS, int K, int VCH, int avs)
 {
     WarpLayout l;
     const int LP = 16 * NS;
@@ -61,6 +62,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(int NS, int K, int VCH)
     o += K * l.PS * 4;
     l.off_cnt = o;  o += 32 * VCH * 4;
     l.off_off = o;  o += 32 * VCH * 4;
+    l.off_av = o;   o += avs ? K * (NS / 2) * 32 * 4 : 0;   // [K][NL][32] high words
     l.total = (o + 15) & ~15;
     return l;
 }
@@ -71,8 +73,8 @@ __host__ __device__ inline int warp_max_chunks(int K, int T_max) { return T_max 
 // words (4 bytes) of workspace per resident CTA: checkpoint columns + exponent per chunk, r image + 1/s per frame
 __host__ __device__ inline long long warp_slot_words(int NS, int K, int VCH, int T_max)
 {
-    const long long nC = warp_max_chunks(K, T_max);
-    return nC * (32LL * NS + 1) + (long long)T_max * (32LL * VCH + 1);
+    const long long nC = warp_max_chunks(K, T_max);          // every section is a multiple of 128 bytes
+    return nC * 32LL * NS + ((nC + 31) & ~31LL) + (long long)T_max * 32LL * VCH + (((long long)T_max + 31) & ~31LL);
 }
 
 __device__ __forceinline__ double hi2d(unsigned hi) { return __hiloint2double((int)hi, 0); }
@@ -161,7 +163,7 @@ __device__ __forceinline__ float warp_sum_transposed(float (&t)[K], int lane)
     return v;
 }
 
-template <int NS, int K, int VCH, int MAXR>
+template <int NS, int K, int VCH, int MAXR, int AVS>
 __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
 {
     static_assert(NS % 2 == 0 && NS >= 2 && NS <= 16, "NS must be even, <= 16");
@@ -174,7 +176,8 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x;
     const int V = P.V, blank = P.blank;
-    const WarpLayout lay = make_warp_layout(NS, K, VCH);
+    const WarpLayout lay = make_warp_layout(NS, K, VCH, AVS);
+    int *av_s = (int *)(smem + lay.off_av) + threadIdx.x;    // [K][NL][32]
     const int PS = lay.PS;
     float *prod = (float *)(smem + lay.off_prod);
     int *lab_s = (int *)(smem + lay.off_lab);
@@ -186,7 +189,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
     const int nCmax = warp_max_chunks(K, P.T_max);
     unsigned *ckw = (unsigned *)P.ckpt + (long long)blockIdx.x * (P.ckpt_stride * 2);   // [nCmax][NS][32] checkpoint high words
     int *eaw = (int *)(ckw + (long long)nCmax * SP);                                // [nCmax] alpha exponent of the chunk
-    unsigned *imgw = (unsigned *)(eaw + nCmax);                                     // [T_max][VCH][32] r high words
+    unsigned *imgw = (unsigned *)(eaw + ((nCmax + 31) & ~31));                      // [T_max][VCH][32] r high words
     float *invw = (float *)(imgw + (long long)P.T_max * VCH * 32);                  // [T_max] 1 / s_t
     const int bl = blank & 31, bs = blank >> 5;
     const double m_first = (lane == 0) ? 0.0 : 1.0;         // lane 0 has no lower neighbour, lane 31 no upper one:
@@ -362,7 +365,10 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         for (int i = 0; i < NS; ++i) a[i] = 0.0;
         if (lane == 0) a[0] = pow2d(kWarpTargetExp);        // virtual column t = -1
         int Ea = -kWarpTargetExp;
-        double lsum = 0.0;                                  // sum of log s_t over the frames this lane is responsible for
+        // sum_t log s_t: lane tt multiplies the s of "its" frame of every chunk into a running fp64 product (s >= 1: the
+        // blank ratio is 1; s < 2^105), renormalised every 8th chunk; ONE log per lane at the end of the sweep
+        double sprod = 1.0;
+        int sexp = 0, sren = 0;
         unsigned hmax = 0u;                                 // largest ratio high word seen (poison detector)
         unsigned rcur[K][VCH];
 
@@ -401,8 +407,15 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             }
             if (t0_next >= 0) load_rows(std::integral_constant<int, K>(), t0_next);
             const float mys = warp_sum_transposed<KK>(sv, lane);
-            const float myinv = 1.f / mys;
-            if (lane < KK) lsum += (double)CTC_ROW_LOG(mys);
+            const float myinv = __frcp_rn(mys);
+            sprod *= (double)((lane < KK) ? mys : 1.f);
+            if (++sren == 8) {
+                sren = 0;
+                const int h = __double2hiint(sprod);
+                const int e = ((h >> 20) & 0x7ff) - 1023;   // (NaN from a poisoned row stays NaN)
+                sexp += e;
+                sprod = __hiloint2double(h - e * (1 << 20), __double2loint(sprod));
+            }
             if (want_grad) {
                 unsigned *ip = imgw + (long long)t0 * (VCH * 32) + lane;
 #pragma unroll
@@ -431,7 +444,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             if (s == S - 1 || s == S - 2) zloc += a[i];
         }
         const double zhat = warp_sum_d(zloc);
-        lsum = warp_sum_d(lsum);
+        const double lsum = warp_sum_d(log(sprod) + (double)sexp * 0.6931471805599453);
         hmax = __reduce_max_sync(kFull, hmax);
         const int Ea_fin = Ea;
         const bool poisoned = (hmax >= 0x7ff00000u);
@@ -483,52 +496,64 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         int Eb = -kWarpTargetExp;
         float chk_dev = 0.f;
 
-        // operands of a backward chunk, loaded by the same lanes that wrote them (plain program order)
-        unsigned cknext[NS], rnext[K][VCH];
-        float invnext = 0.f;
-        int eanext = 0;
-        auto prefetch = [&](auto tag, int t0, int ci) {
-            constexpr int KK = decltype(tag)::value;
+        // Operands of a backward chunk (checkpoint column -> a[], r rows -> rcur, 1/s, chunk exponent), read back by
+        // the lanes that wrote them (plain program order).  They are requested while the PREVIOUS chunk still
+        // computes, into registers that are dead at that point -- a[] after its alpha recompute, rcur after its
+        // gradient rows -- so the prefetch costs no extra live registers (the first version held them in separate
+        // registers, ptxas spilled those, and the spill store waited for the load: 10 % of all stall samples).
+        float myinv = 0.f;
+        int ea_c = 0;
+        unsigned ckr[NS];                                   // (high words only: half the registers of a[] while they wait)
+        auto load_ck = [&](int ci) {
             const unsigned *cp = ckw + (long long)ci * SP + lane;
 #pragma unroll
-            for (int i = 0; i < NS; ++i) cknext[i] = __ldcg(cp + i * 32);
+            for (int i = 0; i < NS; ++i) ckr[i] = __ldcg(cp + i * 32);
+            ea_c = __ldcg(eaw + ci);
+        };
+        auto load_img = [&](auto tag, int t0) {
+            constexpr int KK = decltype(tag)::value;
             const unsigned *ip = imgw + (long long)t0 * (VCH * 32) + lane;
 #pragma unroll
             for (int tt = 0; tt < KK; ++tt)
 #pragma unroll
-                for (int v = 0; v < VCH; ++v) rnext[tt][v] = __ldcg(ip + (tt * VCH + v) * 32);
-            if (lane < KK) invnext = __ldcg(invw + t0 + lane);
-            eanext = __ldcg(eaw + ci);
+                for (int v = 0; v < VCH; ++v) rcur[tt][v] = __ldcg(ip + (tt * VCH + v) * 32);
+            myinv = __ldcg(invw + t0 + (lane & (KK - 1)));
         };
 
-        // backward chunk of KK frames starting at t0: operands are in cknext / rnext / invnext / eanext
-        auto bwd_chunk = [&](auto tag, int t0, int t0_prev, int ci_prev) {
+        // backward chunk of KK frames starting at t0 (operands ready); next: 0 none, 1 one-frame chunk, 2 full chunk
+        auto bwd_chunk = [&](auto tag, int t0, int next, int t0n, int cin) {
             constexpr int KK = decltype(tag)::value;
+            if (next && lane < K * VCH)                     // pull the next chunk's r rows into L2 (they are loaded at the end)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(imgw + (long long)t0n * (VCH * 32) + lane * 32));
+            // The recursion is linear: scaling the checkpoint column by 2^esc (esc = Ea_c + Eb - Ea_fin - ez, the
+            // posterior scale of this chunk) scales every recomputed column, so the products alpha * tb come out
+            // in units of mz directly.  (Entries pushed below 2^-1022 by the scale would need a ratio product of
+            // 2^700 within the chunk to matter again; the range check covers it.)
+            {
+                int esc = ea_c + Eb - Ea_fin - ez;
+                esc = max(-1000, min(esc, 700));
+                const double f = pow2d(esc);
 #pragma unroll
-            for (int i = 0; i < NS; ++i) a[i] = hi2d(cknext[i]);
-#pragma unroll
-            for (int tt = 0; tt < KK; ++tt)
-#pragma unroll
-                for (int v = 0; v < VCH; ++v) rcur[tt][v] = rnext[tt][v];
-            const float myinv = invnext;
-            int esc = eanext + Eb - Ea_fin - ez;
-            if (t0_prev >= 0) prefetch(std::integral_constant<int, K>(), t0_prev, ci_prev);
-            esc = max(-1000, min(esc, 700));
-            const int esc_hi = esc * (1 << 20);
+                for (int i = 0; i < NS; ++i) a[i] = hi2d(ckr[i]) * f;
+            }
 
-            // -- recompute alpha inside the chunk from its checkpoint; keep the label states (scaled high words) --
-            int av[KK][NL];
+            // -- recompute alpha inside the chunk from its checkpoint; keep the label states (high words) --
+            int av[AVS ? 1 : KK][NL];
             int ab[NL];                                     // blank states of the first frame (range check)
 #pragma unroll
             for (int tt = 0; tt < KK; ++tt) {
                 alpha_step(a, rcur[tt]);
 #pragma unroll
-                for (int jj = 0; jj < NL; ++jj) av[tt][jj] = __viaddmax_s32(__double2hiint(a[2 * jj + 1]), esc_hi, 0);
+                for (int jj = 0; jj < NL; ++jj) {
+                    if (AVS) av_s[(tt * NL + jj) * 32] = __double2hiint(a[2 * jj + 1]);
+                    else av[AVS ? 0 : tt][jj] = __double2hiint(a[2 * jj + 1]);
+                }
                 if (tt == 0) {
 #pragma unroll
-                    for (int jj = 0; jj < NL; ++jj) ab[jj] = __viaddmax_s32(__double2hiint(a[2 * jj]), esc_hi, 0);
+                    for (int jj = 0; jj < NL; ++jj) ab[jj] = __double2hiint(a[2 * jj]);
                 }
             }
+            if (next) load_ck(cin);                         // (ckr is dead until the next chunk)
 
             // -- beta over the chunk; products alpha * tb go to shared memory grouped by symbol --
             double q = 0.0;
@@ -544,7 +569,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                         const double s1 = (i + 1 < NS) ? bt[i] + bt[i + 1] : fma(m_last, dn0, bt[i]);
                         const double n2 = (i + 2 < NS) ? bt[i + 2] : dn1;  // (msk[NL] is 0 on lane 31)
                         const double tb = fma(msk[jj + 1], n2, s1);
-                        const double pr = hi2d((unsigned)av[tt][jj]) * tb;
+                        const double pr = hi2d((unsigned)(AVS ? av_s[(tt * NL + jj) * 32] : av[AVS ? 0 : tt][jj])) * tb;
                         if (tt == 0) q += pr;
                         prow[sl[jj]] = (float)pr;
                         bt[i] = tb * pl;
@@ -600,6 +625,8 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                 const float g = (myinv - (one - total)) * P.grad_scale; // p(blank) = 1 / s
                 grads_b[(long long)(t0 + lane) * gst + blank] = g;
             }
+            if (next == 2) load_img(std::integral_constant<int, K>(), t0n);      // rcur / myinv are dead now
+            else if (next == 1) load_img(std::integral_constant<int, 1>(), t0n);
             {   // bt holds column t0.  States above 2*t0 + 1 cannot be reached from the start: zero them
                 const int hi = 2 * t0 + 1;
                 if (hi < S - 1) {
@@ -611,13 +638,20 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             __syncwarp();                                   // gather reads done before the next chunk's products
         };
 
-        for (int u = ntail - 1; u >= 0; --u) {
-            prefetch(std::integral_constant<int, 1>(), nfull * K + u, nfull + u);
-            bwd_chunk(std::integral_constant<int, 1>(), nfull * K + u, -1, 0);
+        if (ntail > 0) {
+            load_ck(nfull + ntail - 1);
+            load_img(std::integral_constant<int, 1>(), T - 1);
+        } else {
+            load_ck(nfull - 1);
+            load_img(std::integral_constant<int, K>(), (nfull - 1) * K);
         }
-        if (nfull > 0) prefetch(std::integral_constant<int, K>(), (nfull - 1) * K, nfull - 1);
+        for (int u = ntail - 1; u >= 0; --u) {
+            const int next = (u > 0) ? 1 : (nfull > 0 ? 2 : 0);
+            bwd_chunk(std::integral_constant<int, 1>(), nfull * K + u, next,
+                      (u > 0) ? nfull * K + u - 1 : (nfull - 1) * K, nfull + u - 1);
+        }
         for (int c = nfull - 1; c >= 0; --c)
-            bwd_chunk(std::integral_constant<int, K>(), c * K, (c >= 1) ? (c - 1) * K : -1, c - 1);
+            bwd_chunk(std::integral_constant<int, K>(), c * K, (c >= 1) ? 2 : 0, (c - 1) * K, c - 1);
 
         if (!(chk_dev <= kCheckTol)) ustat |= UTT_RANGE;
         if (__any_sync(kFull, ustat & UTT_RANGE)) ustat |= UTT_RANGE;

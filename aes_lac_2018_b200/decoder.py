@@ -15,7 +15,39 @@ import torch
 
 from . import _lib
 
-__all__ = ["GreedyDecoder", "greedy_decode_raw", "edit_distance_raw"]
+__all__ = ["GreedyDecoder", "OrderedAlphabet", "greedy_decode_raw", "edit_distance_raw"]
+
+
+class OrderedAlphabet:
+    """Index <-> symbol map in first-appearance order: the `transform` / `inverse_transform` pair of the
+    reference's OrderedLabelEncoder (/root/reference/codes/preprocessing.py:10-80), which `Decoder.__init__`
+    wraps list / set / str alphabets in (codes/decoder.py:39-46).  Host-side bookkeeping only."""
+
+    def __init__(self, symbols):
+        self.classes_ = []
+        self.map_classes_ = {}
+        for c in symbols:
+            if c not in self.map_classes_:
+                self.map_classes_[c] = len(self.classes_)
+                self.classes_.append(c)
+
+    def transform(self, y):
+        try:
+            return [self.map_classes_[c] for c in y]
+        except KeyError as e:
+            raise ValueError(f"y contains previously unseen labels: {e.args[0]!r}") from None
+
+    def inverse_transform(self, y):
+        out = []
+        for i in y:
+            i = int(i)
+            if i < 0 or i >= len(self.classes_):
+                raise ValueError(f"y contains previously unseen labels: {i}")
+            out.append(self.classes_[i])
+        return out
+
+    def __len__(self):
+        return len(self.classes_)
 
 _EDIT_MODES = {"tokens": 0, "cer": 1, "wer": 2}
 
@@ -98,25 +130,55 @@ def edit_distance_raw(hyp_tokens: torch.Tensor, hyp_counts: torch.Tensor, refs, 
 
 class GreedyDecoder:
     """`GreedyDecoder(labels, blank_index=0).decode(probs, sizes)` with the reference's return structure.
-    `labels` is the alphabet in index order (a string / list such as data/labels.en.json) or any object with an
-    `inverse_transform(list_of_indices)` method (the reference's OrderedLabelEncoder)."""
+    `labels` is the alphabet in index order (a string / list such as data/labels.en.json; wrapped in an
+    `OrderedAlphabet` as the reference wraps it in its OrderedLabelEncoder) or any object with `transform` /
+    `inverse_transform` methods (the reference's OrderedLabelEncoder itself)."""
 
     def __init__(self, label_encoder, blank_index: int = 0):
         if isinstance(label_encoder, str):
             label_encoder = list(label_encoder)
+        if isinstance(label_encoder, (set, list, tuple)):    # (decoder.py:42-46 wraps these in an OrderedLabelEncoder)
+            label_encoder = OrderedAlphabet(label_encoder)
         self.label_encoder = label_encoder
         self.blank_index = blank_index
         self.space_index = self._find_space()
 
     def _find_space(self) -> int:
         """Index of ' ' in the alphabet (-1 if it has none: then every transcript is a single word)."""
-        enc = self.label_encoder
         try:
-            if hasattr(enc, "transform"):
-                return int(enc.transform([" "])[0])
-            return list(enc).index(" ")
+            return int(self.label_encoder.transform([" "])[0])
         except (ValueError, KeyError, IndexError):
             return -1
+
+    # -- references to text (decoder.py:100-141; called on the TARGETS at test.py:79 and codes/metrics.py:112) ----
+    def convert_to_strings(self, sequences, sizes=None, remove_repetitions=False, return_offsets=False):
+        """Given a list of numeric sequences, returns the corresponding strings (`[[text], ...]`, and the frame
+        offsets `[[IntTensor], ...]` when asked).  Host-side: the targets are already host tensors."""
+        strings = []
+        offsets = [] if return_offsets else None
+        for i in range(len(sequences)):
+            seq_len = int(sizes[i]) if sizes is not None else len(sequences[i])
+            string, string_offsets = self.process_string(sequences[i], seq_len, remove_repetitions)
+            strings.append([string])                         # one path per utterance
+            if return_offsets:
+                offsets.append([string_offsets])
+        if return_offsets:
+            return strings, offsets
+        return strings
+
+    def process_string(self, sequence, size, remove_repetitions=False):
+        """Drops blanks (and, if asked, symbols equal to the previous FRAME) from `sequence[:size]`; returns the
+        text and the kept positions."""
+        seq = torch.as_tensor(sequence).reshape(-1)[:size].tolist()      # one transfer instead of one .item() per frame
+        kept, offs = [], []
+        for i, cur in enumerate(seq):
+            if cur == self.blank_index:
+                continue
+            if remove_repetitions and i != 0 and cur == seq[i - 1]:
+                continue
+            kept.append(cur)
+            offs.append(i)
+        return self._to_string(kept), torch.IntTensor(offs)
 
     # -- scoring (decoder.py:49-78) ------------------------------------------------------------------------
     @staticmethod
@@ -151,9 +213,7 @@ class GreedyDecoder:
     def _to_string(self, ids):
         if not ids:
             return ""
-        if hasattr(self.label_encoder, "inverse_transform"):
-            return "".join(self.label_encoder.inverse_transform(ids))
-        return "".join(self.label_encoder[i] for i in ids)
+        return "".join(self.label_encoder.inverse_transform(ids))
 
     def decode(self, probs, sizes=None):
         tokens, offsets, counts = greedy_decode_raw(probs, sizes, self.blank_index, want_offsets=True)

@@ -114,11 +114,14 @@ ctcStatus_t get_workspace_size(const int *const label_lengths,
  * optional non-blocking return (A9).
  * ---------------------------------------------------------------------------------------------- */
 
-#define CTC_B200_FLAG_NO_SYNC 0x1u       /* do not synchronise; costs_host/status_host must be NULL */
+#define CTC_B200_FLAG_NO_SYNC 0x1u       /* do not synchronise; costs_host/status_host must be NULL.  Out-of-range
+                                            utterances are still redone in log space (the detour is a device-side
+                                            kernel enqueued behind the fast ones) */
 #define CTC_B200_FLAG_SERIAL_LAUNCHES 0x2u /* keep every kernel on `stream` (no internal fork/join streams) */
 #define CTC_B200_FLAG_NO_BIDIR 0x8u        /* small batches: keep the three-sweep fused kernel instead of the bidirectional path */
 #define CTC_B200_FLAG_NO_FALLBACK 0x4u     /* report out-of-range utterances instead of re-running them in log space */
-/* bits 8..9: variant ladder override (0 auto, 1 throughput, 2 latency, 3 throughput with 8-step chunks) */
+/* bits 8..10: variant ladder override (0 auto, 1 throughput, 2 latency, 3 throughput with 8-step chunks,
+ * 4 warp ladder: one warp per utterance, register-resident -- the large-batch default) */
 
 typedef struct ctcB200Call {
     const float *activations;   /* DEVICE; element (t,b,k) at t*act_stride_t + b*act_stride_b + k */
@@ -144,6 +147,8 @@ typedef struct ctcB200Call {
                                    total ns, SM id, 12 phase cycle counters} -- profiling aid only */
     float *kernel_ms_host;      /* HOST or NULL: device time (CUDA events on `stream`) from the first kernel launch of
                                    this call to the completion of its last one; needs the blocking mode */
+    int *status_device;         /* DEVICE [minibatch] or NULL: per-utterance CTC_B200_UTT_* bits left on the device
+                                   (what a CTC_B200_FLAG_NO_SYNC caller reads later, or never) */
 } ctcB200Call;
 
 /* per-utterance status bits (status_host) */
@@ -279,6 +284,26 @@ typedef struct {
 ctcStatus_t ctc_b200_head_workspace_size(int rows, int features, int classes, size_t *size_bytes);
 ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *call);
 ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *call);
+
+/*
+ * Loss glue on the device.  The reference wraps the loss call in `_sanitize_loss`
+ * (/root/reference/codes/engine.py:19-32: `/ average`, `.sum()`, a host-side `== inf` test that forces a sync,
+ * `0 * loss_sum`), multiplies by a task weight (engine.py:77) and lets `_CTC.backward` rescale the whole T x B x V
+ * gradient tensor by the incoming scalar (one more pass, engine.py:84).  With the scale folded into
+ * ctcB200Call.grad_scale and the cost vector left on the device, two small calls finish the job without a host
+ * round trip; both only enqueue work on `stream`.
+ *
+ * ctc_b200_reduce_costs: loss_device[0] = scale * sum_b costs_device[b] (fp64, fixed order => deterministic).
+ *   If zero_infinite is set and the sum is +-inf, loss_device[0] = 0 and flag_device[0] = 1 (else 0): the guard of
+ *   engine.py:27-30 (which intends "setting loss value to 0"; its `0 * inf` is NaN).  A NaN sum stays NaN.
+ * ctc_b200_scale_gradients: gradients[i] *= f with f = scale_host * (scale_device ? *scale_device : 1), or 0 when
+ *   zero_flag_device && *zero_flag_device.  When f is exactly 1 every CTA returns after reading the two scalars,
+ *   so the common `loss.backward()` costs no pass over the tensor.
+ */
+ctcStatus_t ctc_b200_reduce_costs(const float *costs_device, int minibatch, float scale, int zero_infinite,
+                                  float *loss_device, int *flag_device, CUstream stream);
+ctcStatus_t ctc_b200_scale_gradients(float *gradients, size_t count, float scale_host, const float *scale_device,
+                                     const int *zero_flag_device, CUstream stream);
 
 /* Human-readable description of the last failure on the calling thread ("" if none). */
 const char *ctc_b200_last_error(void);
