@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -256,15 +257,25 @@ bool check(cudaError_t e, const char *what, ctcStatus_t code, ctcStatus_t &out)
     return false;
 }
 
-// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (thread, device, kernel, size) instead of per launch
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when a launch needs more than any earlier one of the same
+// (device, kernel).  The attribute is per-process state, so the record is process-wide and the limit only ever
+// grows: a per-thread record let one thread lower the limit under another thread's larger launch.
 bool ensure_smem_attr(const void *kernel, int smem, ctcStatus_t &st)
 {
     struct Key { const void *k; int dev; int smem; };
-    thread_local std::vector<Key> done;
+    static std::mutex mu;
+    static std::vector<Key> done;
     int dev = 0;
     cudaGetDevice(&dev);
-    for (const Key &e : done)
-        if (e.k == kernel && e.dev == dev && e.smem >= smem) return true;
+    std::lock_guard<std::mutex> lock(mu);
+    for (Key &e : done)
+        if (e.k == kernel && e.dev == dev) {
+            if (e.smem >= smem) return true;
+            if (!check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
+                       "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return false;
+            e.smem = smem;
+            return true;
+        }
     if (!check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return false;
     done.push_back(Key{kernel, dev, smem});

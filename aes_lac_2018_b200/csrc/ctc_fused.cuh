@@ -650,6 +650,7 @@ ctc_fused_kernel(const FusedParams P)
     else if (!z_ok) ustat |= UTT_INF_COST;
     if (tid == 0) {
         const double logz = z_ok ? (log(zhat) + (double)Ea_fin * 0.6931471805599453 - logsum) : -INFINITY;
+        if (z_ok && !(logz == logz)) ustat |= UTT_RANGE;    // a NaN activation poisons the row sums (thread 0 writes the status)
         if (!rev) P.costs[b] = z_ok ? (float)(-logz) : INFINITY;
         if (sweep_only) {
             double *z = P.col_z + (long long)blockIdx.x * 4;

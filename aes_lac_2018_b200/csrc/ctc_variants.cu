@@ -32,7 +32,8 @@ static const Variant kTable[] = {
 #ifdef CTC_WARP_TABLE_INC          // kernel experiments: the table comes from a file (tools/build_alt.sh)
 #include CTC_WARP_TABLE_INC
 #else
-    VW_(2, 8, 128), VW_(4, 8, 144), VW_(6, 8, 168), VW_(8, 8, 168), VW_(10, 4, 168), VW_(12, 4, 168), VW_(14, 4, 184), VW_(16, 4, 200),
+    // (measured per label-length class on B200, profiles/r2_variant_matrix.txt)
+    VW_(2, 16, 128), VW_(4, 8, 128), VW_(6, 8, 168), VW_(8, 8, 168), VWS_(10, 8, 144), VWS_(12, 8, 168), VW_(14, 8, 232), VW_(16, 8, 255),
 #endif
 #else
     // latency: more warps per utterance, fewer states per thread

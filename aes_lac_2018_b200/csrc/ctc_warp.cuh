@@ -46,7 +46,7 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct WarpLayout {
     int PS;                              // product row stride (floats); slot PS-1 is the dump slot of padding labels
-    int off_prod, off_lab, off_slot, off_cnt, off_off, off_av, total;
+    int off_prod, off_lab, off_slot, off_cnt, off_off, off_av, off_stg, total;
 };
 
 // avs: the recomputed alpha of the label states waits for the beta steps in shared memory instead of registers
@@ -63,6 +63,8 @@ __host__ __device__ inline WarpLayout make_warp_layout(int NS, int K, int VCH, i
     l.off_cnt = o;  o += 32 * VCH * 4;
     l.off_off = o;  o += 32 * VCH * 4;
     l.off_av = o;   o += avs ? K * (NS / 2) * 32 * 4 : 0;   // [K][NL][32] high words
+    o = (o + 127) & ~127;
+    l.off_stg = o;  o += (NS * 32 + K * VCH * 32 + K + 1) * 4;   // staged operands of the next backward chunk
     l.total = (o + 15) & ~15;
     return l;
 }
@@ -496,35 +498,58 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         int Eb = -kWarpTargetExp;
         float chk_dev = 0.f;
 
-        // Operands of a backward chunk (checkpoint column -> a[], r rows -> rcur, 1/s, chunk exponent), read back by
-        // the lanes that wrote them (plain program order).  They are requested while the PREVIOUS chunk still
-        // computes, into registers that are dead at that point -- a[] after its alpha recompute, rcur after its
-        // gradient rows -- so the prefetch costs no extra live registers (the first version held them in separate
-        // registers, ptxas spilled those, and the spill store waited for the load: 10 % of all stall samples).
+        // Operands of a backward chunk (checkpoint column, r rows, 1/s per frame, chunk exponent): written by this CTA
+        // during the forward sweep, fetched back with cp.async (16 bytes per lane: the column and the rows of a chunk
+        // are contiguous, so four instructions move all of it) into a shared-memory staging buffer while the
+        // PREVIOUS chunk computes, and read out of it (conflict-free, lane-contiguous) when their chunk starts.  No
+        // registers are held by the prefetch (an earlier version kept them in registers, ptxas spilled those, and
+        // the spill store waited for the load: 10 % of all stall samples) and nothing waits on L2 / DRAM latency at a
+        // chunk boundary (loading them "late, into registers that are dead by then" cost 10 % at K = 8, 25 % at K = 4).
+        unsigned *stg = (unsigned *)(smem + lay.off_stg);   // [NS][32] column | [K][VCH][32] rows | [K] 1/s | [1] exponent
+        auto stage = [&](auto tag, int t0, int ci) {
+            constexpr int KK = decltype(tag)::value;
+            {   // checkpoint column: NS * 128 bytes
+                const char *src = (const char *)(ckw + (long long)ci * SP);
+                char *dst = (char *)stg;
+#pragma unroll
+                for (int o = 0; o < (NS * 128 + 511) / 512; ++o)
+                    if (o * 512 + lane * 16 < NS * 128) cp_async16(dst + o * 512 + lane * 16, src + o * 512 + lane * 16);
+            }
+            {   // r rows: KK * VCH * 128 bytes
+                const char *src = (const char *)(imgw + (long long)t0 * (VCH * 32));
+                char *dst = (char *)(stg + SP);
+#pragma unroll
+                for (int o = 0; o < (KK * VCH * 128 + 511) / 512; ++o)
+                    if (o * 512 + lane * 16 < KK * VCH * 128) cp_async16(dst + o * 512 + lane * 16, src + o * 512 + lane * 16);
+            }
+            if (lane < KK) cp_async4(stg + SP + K * VCH * 32 + lane, invw + t0 + lane);
+            if (lane == KK) cp_async4(stg + SP + K * VCH * 32 + K, eaw + ci);
+            cp_async_commit();
+        };
         float myinv = 0.f;
         int ea_c = 0;
-        unsigned ckr[NS];                                   // (high words only: half the registers of a[] while they wait)
-        auto load_ck = [&](int ci) {
-            const unsigned *cp = ckw + (long long)ci * SP + lane;
-#pragma unroll
-            for (int i = 0; i < NS; ++i) ckr[i] = __ldcg(cp + i * 32);
-            ea_c = __ldcg(eaw + ci);
-        };
-        auto load_img = [&](auto tag, int t0) {
+        // staging buffer -> registers (a[] gets the raw high words; the posterior scale is applied by the caller)
+        auto unstage = [&](auto tag) {
             constexpr int KK = decltype(tag)::value;
-            const unsigned *ip = imgw + (long long)t0 * (VCH * 32) + lane;
+            cp_async_wait_all();
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NS; ++i) a[i] = hi2d(stg[i * 32 + lane]);
 #pragma unroll
             for (int tt = 0; tt < KK; ++tt)
 #pragma unroll
-                for (int v = 0; v < VCH; ++v) rcur[tt][v] = __ldcg(ip + (tt * VCH + v) * 32);
-            myinv = __ldcg(invw + t0 + (lane & (KK - 1)));
+                for (int v = 0; v < VCH; ++v) rcur[tt][v] = stg[SP + (tt * VCH + v) * 32 + lane];
+            myinv = __uint_as_float(stg[SP + K * VCH * 32 + (lane & (KK - 1))]);
+            ea_c = (int)stg[SP + K * VCH * 32 + K];
+            __syncwarp();                                   // everybody has read: the buffer may be refilled
         };
 
         // backward chunk of KK frames starting at t0 (operands ready); next: 0 none, 1 one-frame chunk, 2 full chunk
         auto bwd_chunk = [&](auto tag, int t0, int next, int t0n, int cin) {
             constexpr int KK = decltype(tag)::value;
-            if (next && lane < K * VCH)                     // pull the next chunk's r rows into L2 (they are loaded at the end)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(imgw + (long long)t0n * (VCH * 32) + lane * 32));
+            unstage(tag);
+            if (next == 2) stage(std::integral_constant<int, K>(), t0n, cin);        // lands while this chunk computes
+            else if (next == 1) stage(std::integral_constant<int, 1>(), t0n, cin);
             // The recursion is linear: scaling the checkpoint column by 2^esc (esc = Ea_c + Eb - Ea_fin - ez, the
             // posterior scale of this chunk) scales every recomputed column, so the products alpha * tb come out
             // in units of mz directly.  (Entries pushed below 2^-1022 by the scale would need a ratio product of
@@ -534,7 +559,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                 esc = max(-1000, min(esc, 700));
                 const double f = pow2d(esc);
 #pragma unroll
-                for (int i = 0; i < NS; ++i) a[i] = hi2d(ckr[i]) * f;
+                for (int i = 0; i < NS; ++i) a[i] *= f;
             }
 
             // -- recompute alpha inside the chunk from its checkpoint; keep the label states (high words) --
@@ -553,7 +578,6 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                     for (int jj = 0; jj < NL; ++jj) ab[jj] = __double2hiint(a[2 * jj]);
                 }
             }
-            if (next) load_ck(cin);                         // (ckr is dead until the next chunk)
 
             // -- beta over the chunk; products alpha * tb go to shared memory grouped by symbol --
             double q = 0.0;
@@ -625,8 +649,6 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                 const float g = (myinv - (one - total)) * P.grad_scale; // p(blank) = 1 / s
                 grads_b[(long long)(t0 + lane) * gst + blank] = g;
             }
-            if (next == 2) load_img(std::integral_constant<int, K>(), t0n);      // rcur / myinv are dead now
-            else if (next == 1) load_img(std::integral_constant<int, 1>(), t0n);
             {   // bt holds column t0.  States above 2*t0 + 1 cannot be reached from the start: zero them
                 const int hi = 2 * t0 + 1;
                 if (hi < S - 1) {
@@ -638,13 +660,8 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             __syncwarp();                                   // gather reads done before the next chunk's products
         };
 
-        if (ntail > 0) {
-            load_ck(nfull + ntail - 1);
-            load_img(std::integral_constant<int, 1>(), T - 1);
-        } else {
-            load_ck(nfull - 1);
-            load_img(std::integral_constant<int, K>(), (nfull - 1) * K);
-        }
+        if (ntail > 0) stage(std::integral_constant<int, 1>(), T - 1, nfull + ntail - 1);
+        else stage(std::integral_constant<int, K>(), (nfull - 1) * K, nfull - 1);
         for (int u = ntail - 1; u >= 0; --u) {
             const int next = (u > 0) ? 1 : (nfull > 0 ? 2 : 0);
             bwd_chunk(std::integral_constant<int, 1>(), nfull * K + u, next,

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["CTCLoss", "ctc_loss_raw", "ctc_loss_host", "sanitize_loss", "release_workspaces"]
+__all__ = ["CTCLoss", "ctc_loss_raw", "ctc_loss_host", "sanitize_loss", "reduce_costs", "release_workspaces"]
 
 
 def _as_host_int32(x: torch.Tensor, name: str) -> torch.Tensor:
@@ -159,6 +159,9 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
             raise RuntimeError("ctc_b200_compute: " + _lib.status_string(lib, st))
         if timing is not None:
             timing["kernel_ms"] = float(kms.value)
+        if no_sync:
+            # pinned host labels / lengths are read by DMA after this returns: keep them alive with the result
+            costs._ctc_keepalive = (labels_h, act_lens_h, label_lens_h)
     return costs, grads, status
 
 
@@ -269,6 +272,25 @@ def _scale_gradients(grads: torch.Tensor, scale_host: float = 1.0, scale_device:
         raise RuntimeError("ctc_b200_scale_gradients: " + _lib.status_string(lib, st))
 
 
+def reduce_costs(costs: torch.Tensor, scale: float = 1.0, zero_infinity: bool = False):
+    """Device-side `scale * costs.sum()` (fp64 accumulation in a fixed order, one tiny kernel on the current stream):
+    returns (loss: CUDA float32 tensor of shape [1], flag: CUDA int32 [1], 1 iff `zero_infinity` replaced a +-inf sum
+    by 0).  This is the operand of the path's single collective (the scalar NCCL loss sum) -- it never visits the host."""
+    lib = _lib.load()
+    if not costs.is_cuda or costs.dtype != torch.float32:
+        raise TypeError("costs must be a CUDA float32 tensor (ctc_loss_raw(..., no_sync=True) returns one)")
+    costs = costs.contiguous()
+    dev = costs.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = lib.ctc_b200_reduce_costs(costs.data_ptr(), costs.numel(), float(scale), 1 if zero_infinity else 0,
+                                       loss.data_ptr(), flag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+    if st != _lib.CTC_STATUS_SUCCESS:
+        raise RuntimeError("ctc_b200_reduce_costs: " + _lib.status_string(lib, st))
+    return loss, flag
+
+
 class _FusedCTC(torch.autograd.Function):
     """Loss glue fused around the engine call: `scale` (1/average * task weight) goes into the
     gradient epilogue of the kernel, the cost vector is summed and inf-guarded on the device, nothing is read back:
@@ -276,21 +298,14 @@ class _FusedCTC(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, acts, labels, act_lens, label_lens, scale, blank, zero_infinity):
-        lib = _lib.load()
         want_grad = bool(ctx.needs_input_grad[0])
         costs, grads, status = ctc_loss_raw(acts, labels, act_lens, label_lens, blank=blank, want_grad=want_grad,
                                             grad_scale=scale, no_sync=True)
-        dev = costs.device
-        loss = torch.empty((), dtype=torch.float32, device=dev)
-        flag = torch.empty(1, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            st = lib.ctc_b200_reduce_costs(costs.data_ptr(), costs.numel(), float(scale), 1 if zero_infinity else 0,
-                                           loss.data_ptr(), flag.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
-        if st != _lib.CTC_STATUS_SUCCESS:
-            raise RuntimeError("ctc_b200_reduce_costs: " + _lib.status_string(lib, st))
+        # (the kernel already folded `scale` into the gradient; the costs are unscaled)
+        loss, flag = reduce_costs(costs, scale, zero_infinity)
         ctx.grads, ctx.flag, ctx.used = grads, flag, False
         ctx.mark_non_differentiable(status)
-        return loss, status
+        return loss.reshape(()), status
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_status):

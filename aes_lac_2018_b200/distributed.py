@@ -59,6 +59,26 @@ def all_reduce_loss(local_loss: torch.Tensor, group=None) -> torch.Tensor:
     return t
 
 
+def sharded_loss_step(acts, labels, act_lens, label_lens, blank: int = 0, grad_scale: float = 1.0, want_grad: bool = True,
+                      group=None, mode: str = "auto"):
+    """One step of the sharded path with NOTHING leaving the device: the engine runs on this rank's shard without a
+    host synchronisation (CTC_B200_FLAG_NO_SYNC), the per-utterance costs are summed by a kernel on the same
+    stream, and that one fp32 is all-reduced over NCCL/NVLink -- stream-ordered behind the kernels (SURVEY.md
+    section 5: "the scalar ncclAllReduce enqueued on the compute stream right after the beta/grad kernel").
+    Returns (global_loss [1] CUDA, local_loss [1] CUDA, grads [T,B,V] CUDA or None, status [B] CUDA int32).
+    Round 1 copied the cost vector to the host, summed it there and copied the sum back before the collective
+    (one blocking sync per step: the named limiter of its 1 -> 8 GPU curve)."""
+    from .ctc_loss import ctc_loss_raw, reduce_costs
+    costs, grads, status = ctc_loss_raw(acts, labels, act_lens, label_lens, blank=blank, want_grad=want_grad,
+                                        grad_scale=grad_scale, mode=mode, no_sync=True)
+    local, _ = reduce_costs(costs, 1.0, False)
+    total = local
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        total = local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    return total, local, grads, status
+
+
 class ShardedCTCLoss(torch.nn.Module):
     """CTCLoss over this rank's shard of the batch; forward returns (global_loss[1], local_loss[1]).
     Backward through `local_loss` gives this rank's gradients; nothing else is communicated."""

@@ -160,6 +160,63 @@ def run_reference(args, rank: int, world: int):
     print(json.dumps(out), flush=True)
 
 
+def measure_link(dev, nbytes: int = 256 << 20):
+    """Pinned host <-> device copy rates on this box (GB/s): H2D alone, D2H alone, both directions at once."""
+    import torch
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            fn()
+            torch.cuda.synchronize(dev)
+            best = min(best, time.perf_counter() - t0)
+        return nbytes / best / 1e9
+
+    def up():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+
+    def down():
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+
+    def both():
+        up()
+        down()
+
+    up(); down()
+    return {"h2d": timed(up), "d2h": timed(down), "duplex_per_direction": timed(both)}
+
+
+def make_peaky_ragged(batch: int, seed: int):
+    """Trained-model-like posteriors (SURVEY.md 8d "peaky" variant): N(0,1) logits, +6 on the blank for 70 % of the
+    frames and +6 on an aligned label for the rest, ragged act_lens in [0.6 T, T] with L <= T/4."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    acts = torch.randn(T, batch, V, generator=g, dtype=torch.float32)
+    act_lens = torch.randint(int(0.6 * T), T + 1, (batch,), generator=g, dtype=torch.int32)
+    label_lens = torch.minimum(torch.randint(LMIN, LMAX + 1, (batch,), generator=g, dtype=torch.int32), act_lens // 4)
+    labels = torch.randint(1, V, (int(label_lens.sum()),), generator=g, dtype=torch.int32)
+    blank_frames = torch.rand(T, batch, generator=g) < 0.7
+    acts[..., 0] += 6.0 * blank_frames
+    offs = torch.cumsum(label_lens.long(), 0) - label_lens.long()
+    # frame t of utterance b is "aligned" to label floor(t * L / T_b)
+    t_idx = torch.arange(T).unsqueeze(1)
+    pos = torch.clamp((t_idx * label_lens.unsqueeze(0).long()) // act_lens.unsqueeze(0).long().clamp(min=1),
+                      max=(label_lens.long() - 1).clamp(min=0).unsqueeze(0))
+    sym = labels.long()[(offs.unsqueeze(0) + pos).clamp(max=max(labels.numel() - 1, 0))]
+    bump = (~blank_frames) & (label_lens.unsqueeze(0) > 0)
+    acts.scatter_add_(2, sym.unsqueeze(2), (6.0 * bump).unsqueeze(2).to(acts.dtype))
+    return acts, labels, act_lens, label_lens
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,6 +227,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256, help="utterances per CPU-reference step")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline numbers only (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -184,7 +242,7 @@ def main():
     import torch
     import torch.distributed as dist
     from aes_lac_2018_b200 import _lib, build as _build, ctc_loss_host, ctc_loss_raw
-    from aes_lac_2018_b200.distributed import all_reduce_loss
+    from aes_lac_2018_b200.distributed import shard_bounds, shard_problem, sharded_loss_step
     if not os.path.exists(_build.LIB):
         # harness convenience only (never taken when the in-tree .so travelled with the snapshot); the engine itself
         # never builds or falls back -- it fails loudly.  Local rank 0 builds, the other ranks wait for the file.
@@ -215,14 +273,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    loss_total = None
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    last = {}
 
     def step():
-        nonlocal loss_total
-        costs, grads, _ = ctc_loss_raw(acts, labels, act_lens, label_lens, want_grad=True)
-        local = costs.double().sum().to(torch.float32).reshape(1)
-        loss_total = all_reduce_loss(local)            # scalar NCCL sum over NVLink when world > 1
-        return grads
+        # The public non-blocking path: engine (NO_SYNC) -> device-side cost sum -> scalar NCCL all-reduce, all
+        # stream-ordered; nothing is read back inside the timed region except once, after its last step.
+        total, local, grads, status = sharded_loss_step(acts, labels, act_lens, label_lens, want_grad=True)
+        last.update(total=total, local=local, grads=grads, status=status)
 
     # ---- device-resident throughput (value) ----
     for _ in range(args.warmup):
@@ -236,15 +299,27 @@ def main():
             step()
         e1.record()
         barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_max = max_over_ranks(e0.elapsed_time(e1))
     launches = _lib.launch_count() - n0
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     value = B * world * args.steps / (ms_max * 1e-3)
 
-    # ---- kernel-only device time of the fused launches (roofline) ----
+    # ---- what the step computed: the all-reduced loss must equal the fp64 sum of the gathered local sums ----
+    loss_total = float(last["total"].item())
+    local_sum = float(last["local"].item())
+    status_or = 0
+    for bit in (1, 2, 4, 8, 16):
+        if bool((last["status"] & bit).any().item()):
+            status_or |= bit
+    gathered = [local_sum]
+    if world > 1:
+        obj = [None] * world
+        dist.all_gather_object(obj, local_sum)
+        gathered = [float(x) for x in obj]
+    loss_fp64 = float(sum(gathered))
+    loss_ok = abs(loss_total - loss_fp64) <= 1e-6 * abs(loss_fp64)
+    assert loss_ok, f"all-reduced loss {loss_total} != sum of local sums {loss_fp64}"
+
+    # ---- kernel-only device time of one engine call (roofline) ----
     # CUDA events recorded by the library on the launching stream: first kernel launch of a call -> completion
     # of the last one (the variant launches overlap on forked streams and are joined back before the end event).
     kt = []
@@ -254,6 +329,16 @@ def main():
         kt.append(tm["kernel_ms"])
     kernel_ms = sorted(kt)[len(kt) // 2]
 
+    # ---- the blocking drop-in call (what `warpctc_pytorch.CTCLoss` does: costs read back every step) ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(min(args.steps, 10)):
+        ctc_loss_raw(acts, labels, act_lens, label_lens, want_grad=True)
+    e1.record()
+    barrier()
+    blocking_ms = max_over_ranks(e0.elapsed_time(e1)) / min(args.steps, 10)
+
     # ---- end to end with host buffers (e2e) ----
     pinned = acts_h.pin_memory()
     grads_h = torch.empty((T, B, V), dtype=torch.float32, pin_memory=True)
@@ -261,38 +346,112 @@ def main():
         ctc_loss_host(pinned, labels, act_lens, label_lens, grads_out=grads_h)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall = time.perf_counter()
     e0.record()
     for _ in range(args.e2e_steps):
         costs_h, _, _ = ctc_loss_host(pinned, labels, act_lens, label_lens, grads_out=grads_h)
-        local = costs_h.double().sum().to(torch.float32).reshape(1)
-        all_reduce_loss(local)
+        local = costs_h.double().sum().to(torch.float32).reshape(1).to(dev)
+        if world > 1:
+            dist.all_reduce(local)
     e1.record()
     barrier()
-    t_wall = time.perf_counter() - t_wall
-    e2e_ms = max(e0.elapsed_time(e1), 0.0)
-    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.e2e_steps / (float(t.item()) * 1e-3)
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+    e2e_value = B * world * args.e2e_steps / (e2e_ms * 1e-3)
     h2d = acts_h.numel() * 4 + labels.numel() * 4 + 2 * B * 4
     d2h = grads_h.numel() * 4 + B * 4 + B * 4
+    link = measure_link(dev) if not args.no_extras else None
+    del pinned, grads_h
 
-    # ---- BASELINE configs[1] literally (B=32): latency regime, reported beside the headline ----
-    a32_h, l32, al32, ll32 = make_problem(32, seed=99)
-    a32 = a32_h.to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    lat = []
-    for i in range(8):
-        flush.zero_()                                  # inputs are smaller than L2: flush it between calls
+    extras = {}
+    if not args.no_extras:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def timed_calls(fn, reps=8, skip=3, do_flush=True):
+            ts = []
+            for i in range(reps):
+                if do_flush:
+                    flush.zero_()                      # inputs smaller than L2: flush it between calls
+                k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                k0.record()
+                fn()
+                k1.record()
+                torch.cuda.synchronize()
+                if i >= skip:
+                    ts.append(k0.elapsed_time(k1))
+            return sorted(ts)[len(ts) // 2]
+
+        # BASELINE configs[1] literally (B=32): the latency regime the reference trains in
+        a32_h, l32, al32, ll32 = make_problem(32, seed=99)
+        a32 = a32_h.to(dev)
+        lat_ms = timed_calls(lambda: ctc_loss_raw(a32, l32, al32, ll32, want_grad=True))
+        lat_nosync_ms = timed_calls(lambda: sharded_loss_step(a32, l32, al32, ll32))
+        extras["configs1_b32_latency"] = {
+            "ms_per_call": lat_ms, "utterances_per_s": 32 / (lat_ms * 1e-3), "ms_per_call_non_blocking": lat_nosync_ms,
+            "note": "BASELINE configs[1] literally (B=32, the reference's training batch size): bound by the T-serial chain "
+                    "(750 dependent steps), not by bytes; L2 flushed between calls"}
+
+        # BASELINE configs[3]: B=1024, T=1500 split over the N ranks (strong scaling); every rank also times the whole
+        # batch alone, so the efficiency t(1) / (N * t(N)) comes from one run on one box
+        g = torch.Generator().manual_seed(777)
+        B4, T4 = 1024, 1500
+        a4 = torch.randn(T4, B4, V, generator=g, dtype=torch.float32)
+        ll4 = torch.randint(LMIN, LMAX + 1, (B4,), generator=g, dtype=torch.int32)
+        al4 = torch.full((B4,), T4, dtype=torch.int32)
+        lab4 = torch.randint(1, V, (int(ll4.sum()),), generator=g, dtype=torch.int32)
+        a4d = a4.to(dev)
+        t_full = timed_calls(lambda: ctc_loss_raw(a4d, lab4, al4, ll4, want_grad=True, no_sync=True), do_flush=False)
+        lo, hi = shard_bounds(B4, world, rank)
+        lab_s, al_s, ll_s = shard_problem(lab4, al4, ll4, lo, hi)
+        a4s = a4d[:, lo:hi].contiguous()
+        for _ in range(3):
+            sharded_loss_step(a4s, lab_s, al_s, ll_s)
+        barrier()
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         k0.record()
-        ctc_loss_raw(a32, l32, al32, ll32, want_grad=True)
+        for _ in range(5):
+            sharded_loss_step(a4s, lab_s, al_s, ll_s)
         k1.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            lat.append(k0.elapsed_time(k1))
-    lat_ms = sorted(lat)[len(lat) // 2]
+        barrier()
+        t_shard = max_over_ranks(k0.elapsed_time(k1) / 5)
+        t_full = max_over_ranks(t_full)
+        extras["c4_strong"] = {
+            "workload": "BASELINE configs[3]: B=1024, T=1500, V=29, L~U{50..200}, batch split over the ranks, scalar NCCL loss sum",
+            "n_gpus": world, "ms_per_step": t_shard, "utterances_per_s": B4 / (t_shard * 1e-3),
+            "single_gpu_ms_same_box": t_full, "efficiency_vs_1gpu": t_full / (world * t_shard),
+            "note": "1024/N utterances per GPU: below one wave of resident warps for N >= 2, so the step time approaches "
+                    "the T-serial chain of the longest transcript (1500 dependent steps)"}
+        del a4, a4d, a4s
+
+        # trained-model-like activations, ragged lengths: how often does the log-space detour fire?
+        ap_h, lp, alp, llp = make_peaky_ragged(B, seed=555 + rank)
+        ap_d = ap_h.to(dev)
+        pk_ms = timed_calls(lambda: ctc_loss_raw(ap_d, lp, alp, llp, want_grad=True, no_sync=True), reps=6, do_flush=False)
+        _, _, st_p = ctc_loss_raw(ap_d, lp, alp, llp, want_grad=True)
+        extras["peaky_ragged"] = {
+            "workload": f"B={B}, blank +6 on 70 % of frames / aligned label +6 otherwise, act_lens in [0.6 T, T], L <= T/4",
+            "ms_per_call": pk_ms, "utterances_per_s": B / (pk_ms * 1e-3),
+            "logspace_detour_rate": float((st_p & 16).ne(0).float().mean().item()),
+            "infeasible": int((st_p & 1).ne(0).sum().item()), "range_flag_left": int((st_p & 8).ne(0).sum().item())}
+        del ap_h, ap_d
+
+        # a neutral GPU arm: torch.nn.functional.ctc_loss (fp32, log_softmax + autograd backward) on the same shape
+        try:
+            import torch.nn.functional as F
+            Bt = 1024
+            x = acts[:, :Bt].detach().clone().requires_grad_()
+            tl = label_lens[:Bt].long()
+            tg = labels[:int(tl.sum())].long().to(dev)
+            il = act_lens[:Bt].long()
+
+            def torch_step():
+                x.grad = None
+                F.ctc_loss(F.log_softmax(x, -1), tg, il, tl, blank=0, reduction="sum").backward()
+
+            tms = timed_calls(torch_step, reps=5, skip=2, do_flush=False)
+            extras["torch_ctc_loss_gpu"] = {"batch": Bt, "ms_per_step": tms, "utterances_per_s": Bt / (tms * 1e-3),
+                                            "what": "torch.nn.functional.ctc_loss fp32 (log_softmax + backward) on this GPU, "
+                                                    "same T, V, L distribution; a neutral GPU implementation, not the reference's"}
+        except Exception as e:  # noqa: BLE001
+            extras["torch_ctc_loss_gpu"] = {"unavailable": repr(e)[:200]}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -301,11 +460,13 @@ def main():
         else:
             peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch_set")
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch_set")
+                traffic_src = "NOT measured in this run: " + tj.get("source", "profiles/r2_traffic.json")
             except Exception:  # noqa: BLE001
                 traffic = None
         out = {
@@ -315,27 +476,32 @@ def main():
             "config": {"workload": f"BASELINE configs[1] shape (T={T}, V={V}, L~U{{{LMIN}..{LMAX}}}, fp32 activations, "
                                    f"randn logits) at throughput batch {B} utterances per GPU",
                        "batch_per_gpu": B, "global_batch": B * world, "T": T, "V": V, "label_len": [LMIN, LMAX],
-                       "parallelism": f"batch-sharded x{world}, scalar NCCL loss sum",
+                       "parallelism": f"batch-sharded x{world}, scalar NCCL loss sum enqueued behind the kernels (no host round trip)",
+                       "api": "aes_lac_2018_b200.distributed.sharded_loss_step: ctc_b200_compute(NO_SYNC) + ctc_b200_reduce_costs + all_reduce",
                        "l2": f"inputs larger than L2 ({acts.numel() * 4 >> 20} MiB activations + equal gradients per GPU)",
                        "host_side": "labels and lengths in pinned host memory (engine.py:16 keeps them on the CPU)"},
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "ctc_b200_compute_host (pinned host activations in, host gradients + costs out)",
-                    "steps": args.e2e_steps},
+                    "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps, "link_gbs": link,
+                    "link_bound_utt_per_s": (B / (max(h2d, d2h) / (link["duplex_per_direction"] * 1e9)) * world) if link else None},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "ctc_fused_kernel<NS,1,8,1> (all variant launches of one call, overlapped on forked streams)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "ctc_warp_kernel<NS,8,1,*> (the variant launches of one call, overlapped on forked streams)",
                          "algorithmic_bytes_per_call": alg_bytes, "kernel_ms_per_call": kernel_ms},
-            "configs1_b32_latency": {"ms_per_call": lat_ms, "utterances_per_s": 32 / (lat_ms * 1e-3),
-                                     "note": "BASELINE configs[1] literally (B=32): T-serial chain bound; L2 flushed between calls"},
-            "loss_check": float(loss_total.item()) if loss_total is not None else None,
+            "blocking_dropin": {"ms_per_step": blocking_ms, "utterances_per_s": B * world / (blocking_ms * 1e-3),
+                                "what": "same engine call with upstream's blocking contract (costs and status read back every step)"},
+            "loss_check": {"all_reduced": loss_total, "fp64_sum_of_local_sums": loss_fp64, "equal": loss_ok, "status_bits_seen": status_or},
         }
+        out.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_run(args.cpu_sample, min_seconds=10.0, max_reps=40)
             out["cpu_baseline"] = {"value": cb["utt_per_s"], "unit": "utterances/s", "cores": cb["cores"], "kind": "port",
                                    "sample": f"{args.cpu_sample} utterances of the same workload x {cb['reps']} repetitions "
-                                             f"(best {cb['best_s']:.3f} s), fp32 C/OpenMP restatement of warp-ctc's CPU path"}
+                                             f"(best {cb['best_s']:.3f} s), fp32 C/OpenMP restatement of warp-ctc's CPU path "
+                                             "(a port: warp-ctc itself is absent; OpenMP schedule(dynamic,1) where upstream "
+                                             "uses a plain parallel for, which favours this arm slightly)"}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -87,7 +87,9 @@ def test_no_sync_path_and_device_detour():
         torch.cuda.synchronize()
         assert torch.equal(c_d.cpu(), c_b) and torch.equal(g_d, g_b) and torch.equal(s_d.cpu(), s_b), mode
         st = s_b.numpy()
-        assert st[1] & 0x10 and st[3] & 0x10 and not (st & 0x8).any(), (mode, st)
+        assert st[1] & 0x10 and not (st & 0x8).any(), (mode, st)             # (utterance 3 is inside the warp ladder's range)
+        if mode != "warp":
+            assert st[3] & 0x10, (mode, st)
         rel = np.abs(c_b.numpy() - oc) / np.maximum(1.0, np.abs(oc))
         assert rel.max() <= LOSS_RTOL and np.abs(g_b.cpu().numpy() - og).max() <= GRAD_ATOL, mode
 

@@ -385,16 +385,24 @@ def test_two_threads_two_streams():
 
 @pytest.mark.parametrize("mode", ["warp", "latency", "throughput8"])
 def test_against_fp32_warpctc_cpu_port_small_t(mode):
-    """north_star: "match the reference's warp-ctc ... cross-checked against float64".  At T <= 30 the fp32 log-space
-    arithmetic of warp-ctc's CPU path (oracle/warpctc_cpu.c) is itself within 1e-5 of float64, so the CUDA path can
-    be compared with it directly at the north_star tolerances."""
-    from oracle import warpctc_cpu
-    for seed, (T, B, V, lmax) in enumerate([(30, 16, 29, 12), (24, 9, 43, 8), (12, 5, 29, 5), (30, 4, 29, 14)]):
+    """north_star: "match the reference's warp-ctc ... cross-checked against float64".  warp-ctc's CPU arithmetic
+    (fp32 log space, oracle/warpctc_cpu.c) subtracts numbers of size |log Z| ~ 2.8 T, so its own distance to float64
+    grows with T: 2e-6 at T = 12, 1.6e-5 at T = 30 (measured in this test).  Up to T = 12 the CUDA path is therefore
+    compared with it directly at the north_star tolerances; at T = 24 / 30 the bound is 1e-5 plus the port's own
+    measured distance to float64 (triangle inequality), and the CUDA path must still be within 1e-5 of float64."""
+    from oracle import ctc_f64, warpctc_cpu
+    shapes = [(12, 16, 29, 5), (10, 9, 43, 4), (8, 5, 29, 3), (12, 4, 29, 6), (30, 16, 29, 12), (24, 9, 43, 8)]
+    for seed, (T, B, V, lmax) in enumerate(shapes):
         acts, labels, al, ll = synth_problem(300 + seed, T, B, V, 0, lmax, tmin=max(1, T // 2))
         wc, wg = warpctc_cpu.ctc_batch(acts, labels, al, ll)
+        oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
         costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
+        port_err = float(np.abs(wg - og).max())
+        slack = 0.0 if T <= 12 else port_err
         rel = np.abs(costs - wc) / np.maximum(1.0, np.abs(wc))
-        assert rel.max() <= LOSS_RTOL and np.abs(grads - wg).max() <= GRAD_ATOL, (mode, seed, rel.max(), np.abs(grads - wg).max())
+        d = float(np.abs(grads - wg).max())
+        assert rel.max() <= LOSS_RTOL and d <= GRAD_ATOL + slack, (mode, seed, T, rel.max(), d, port_err)
+        _assert_close(costs, grads, oc, og, f"small-T/{mode}/{seed}")
 
 
 def test_config3_full_size():
