@@ -41,7 +41,8 @@ constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBidirMaxB = 96;              // bidirectional (two sweeps + combine) path for batches up to this size ...
 constexpr size_t kBidirMaxBytes = 192u << 20;   // ... and up to this many bytes of spilled columns
-constexpr int kWarpMinB = 2048;             // automatic ladder choice: warp ladder from this batch size
+constexpr int kWarpMinB = 1024;             // automatic ladder choice: warp ladder from this batch size (measured crossover,
+                                            // profiles/r2_crossover.txt)
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
 constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)
 constexpr int kMaxLaunches = 16;
