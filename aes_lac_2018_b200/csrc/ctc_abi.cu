@@ -217,7 +217,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
 // back to back (each variant's grid alone rarely fills 148 SMs).  Forked from / joined to the caller's
 // stream with events; created lazily per (thread, device).
 constexpr int kAuxStreams = 6;
-constexpr int kPipeStreams = 3;
+constexpr int kPipeStreams = 3;               // copy-in, kernels, copy-out
+constexpr int kPipeBuffers = 4;               // buffer sets of the host-buffer pipeline
 struct AuxStreams {
     bool ready = false;
     cudaStream_t s[kAuxStreams];
@@ -225,6 +226,17 @@ struct AuxStreams {
     cudaStream_t pipe[kPipeStreams];           // host-buffer entry point: H2D / compute / D2H pipeline
     cudaEvent_t pipe_fork, pipe_join[kPipeStreams];
     cudaEvent_t t0, t1;                        // timing events (kernel_ms_host)
+    std::vector<cudaEvent_t> ev_in, ev_k, ev_out;      // host-buffer pipeline: per-chunk stage completion events
+    bool chunk_events(size_t n)
+    {
+        while (ev_in.size() < n) {
+            cudaEvent_t e[3];
+            for (int i = 0; i < 3; ++i)
+                if (cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            ev_in.push_back(e[0]); ev_k.push_back(e[1]); ev_out.push_back(e[2]);
+        }
+        return true;
+    }
 };
 thread_local int *g_status_dev_override = nullptr;      // set by the host-buffer entry point around run()
 thread_local AuxStreams g_aux[16];
@@ -490,12 +502,14 @@ struct HostPlan {
 ctcStatus_t make_host_plan(const int *label_lengths, const int *input_lengths, int V, int B, int T, bool want_grad,
                            int n_chunks, HostPlan &hp)
 {
-    if (n_chunks <= 0) n_chunks = (B >= 2048) ? 8 : (B >= 256 ? 4 : 1);
+    // automatic: slices of 256 utterances (measured optimum on B200, profiles/r2_e2e_sweep.txt: finer slices shorten the
+    // fill and drain of the pipeline, coarser ones amortise the per-slice host work of the inner call)
+    if (n_chunks <= 0) n_chunks = std::max(1, std::min(64, B / 256));
     n_chunks = std::max(1, std::min(n_chunks, B));
     hp.n_chunks = n_chunks;
     hp.Bc = (B + n_chunks - 1) / n_chunks;
     hp.n_chunks = (B + hp.Bc - 1) / hp.Bc;
-    hp.n_buf = std::min(hp.n_chunks, kPipeStreams);
+    hp.n_buf = std::min(hp.n_chunks, kPipeBuffers);
     for (int c = 0; c < hp.n_chunks; ++c) {
         const int lo = c * hp.Bc, n = std::min(hp.Bc, B - lo);
         size_t need = 0;
@@ -538,21 +552,34 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
         for (int b = 0; b < n; ++b) s += c.label_lengths[lo + b];
         lab_off[ch + 1] = lab_off[ch] + s;
     }
+    // Three stage streams -- copy-in, kernels, copy-out -- chained per chunk by events, over n_buf buffer sets: the
+    // H2D engine runs back to back as long as a set is free, whatever the other two stages are doing.  (Round 1 put
+    // the three stages of a chunk on ONE stream per set: the next upload into a set waited for the previous
+    // download out of it, and the pipeline reached ~60 % of the duplex link rate.)
+    cudaStream_t s_in = aux->pipe[0], s_k = aux->pipe[1], s_out = aux->pipe[2];
+    if (!aux->chunk_events((size_t)hp.n_chunks)) return fail(CTC_STATUS_EXECUTION_FAILED, "could not create pipeline events");
     if (!check(cudaEventRecord(aux->pipe_fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
-    for (int i = 0; i < hp.n_buf; ++i)
+    for (int i = 0; i < kPipeStreams; ++i)
         if (!check(cudaStreamWaitEvent(aux->pipe[i], aux->pipe_fork, 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     const size_t row_all = sizeof(float) * (size_t)B * V;
     for (int ch = 0; ch < hp.n_chunks; ++ch) {
         const int lo = ch * hp.Bc, n = std::min(hp.Bc, B - lo);
         const int set = ch % hp.n_buf;
-        cudaStream_t ps = aux->pipe[set];
         char *base = ws + hp.off_sets + hp.set_bytes * set;
         float *d_acts = (float *)base;
         float *d_grads = want_grad ? (float *)(base + hp.acts_bytes) : nullptr;
         void *inner = base + hp.acts_bytes * (want_grad ? 2 : 1);
         const size_t row_c = sizeof(float) * (size_t)n * V;
+        // copy-in: the set's activation buffer is free once the kernels of its previous tenant are done
+        if (ch >= hp.n_buf &&
+            !check(cudaStreamWaitEvent(s_in, aux->ev_k[ch - hp.n_buf], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
         if (!check(cudaMemcpy2DAsync(d_acts, row_c, c.activations + (size_t)lo * V, row_all, row_c, T,
-                                     cudaMemcpyHostToDevice, ps), "H2D activations", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+                                     cudaMemcpyHostToDevice, s_in), "H2D activations", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        if (!check(cudaEventRecord(aux->ev_in[ch], s_in), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        // kernels: need the upload, and the set's gradient buffer drained by the previous tenant's download
+        if (!check(cudaStreamWaitEvent(s_k, aux->ev_in[ch], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        if (ch >= hp.n_buf && want_grad &&
+            !check(cudaStreamWaitEvent(s_k, aux->ev_out[ch - hp.n_buf], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
         ctcB200Call k;
         std::memset(&k, 0, sizeof(k));
         k.activations = d_acts; k.act_stride_t = (long long)n * V; k.act_stride_b = V;
@@ -564,17 +591,22 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
         k.grad_scale = c.grad_scale;
         k.costs_device = d_costs + lo;
         k.workspace = inner; k.workspace_bytes = hp.inner_ws;
-        k.stream = (CUstream)ps;
-        k.flags = (c.flags & ~0xffu) | CTC_B200_FLAG_NO_SYNC;
+        k.stream = (CUstream)s_k;
+        k.flags = (c.flags & 0x700u) | CTC_B200_FLAG_NO_SYNC;
         g_status_dev_override = d_status + lo;
         st = run(k);
         g_status_dev_override = nullptr;
         if (st != CTC_STATUS_SUCCESS) return st;
-        if (want_grad &&
-            !check(cudaMemcpy2DAsync(c.gradients + (size_t)lo * V, row_all, d_grads, row_c, row_c, T,
-                                     cudaMemcpyDeviceToHost, ps), "D2H gradients", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+        if (!check(cudaEventRecord(aux->ev_k[ch], s_k), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        // copy-out
+        if (want_grad) {
+            if (!check(cudaStreamWaitEvent(s_out, aux->ev_k[ch], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+            if (!check(cudaMemcpy2DAsync(c.gradients + (size_t)lo * V, row_all, d_grads, row_c, row_c, T,
+                                         cudaMemcpyDeviceToHost, s_out), "D2H gradients", CTC_STATUS_MEMOPS_FAILED, st)) return st;
+            if (!check(cudaEventRecord(aux->ev_out[ch], s_out), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+        }
     }
-    for (int i = 0; i < hp.n_buf; ++i) {
+    for (int i = 0; i < kPipeStreams; ++i) {
         if (!check(cudaEventRecord(aux->pipe_join[i], aux->pipe[i]), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
         if (!check(cudaStreamWaitEvent(stream, aux->pipe_join[i], 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     }

@@ -300,15 +300,61 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                 }
             }
             __syncwarp();
+            // Which slot of its symbol's segment a label gets decides the bank its product is STORED to: round jj of a
+            // frame has lane l store label l*NL + jj, and two labels of a round that land in the same bank cost a
+            // replay (random assignment: ~3 wavefronts per store, 11-18 replays per utterance-timestep, a fifth of all
+            // shared-memory wavefronts).  One lane assigns the slots greedily in label order -- first free slot of the
+            // segment whose bank is still unused in the label's round -- which removes most of them; ~12 instructions
+            // per label, once per utterance.  (Segments longer than 32 slots take the plain order.)
+            unsigned *free_s = (unsigned *)(slot_s + LP);   // [32 * VCH] free-slot masks (prologue only)
+            int big = 0;
 #pragma unroll
             for (int v = 0; v < VCH; ++v) {
                 const int k = lane + 32 * v;
                 kcnt[v] = cnt_s[k];
                 koff[v] = off_s[k];
-                int q = koff[v];
-                if (kcnt[v])
-                    for (int j = 0; j < L; ++j)
-                        if (lab_s[j] == k) slot_s[j] = q++;
+                free_s[k] = (kcnt[v] >= 32) ? 0xffffffffu : ((1u << kcnt[v]) - 1u);
+                big |= (kcnt[v] > 32);
+            }
+            big = __any_sync(kFull, big);
+            __syncwarp();
+            if (!big) {
+                if (lane == 0) {
+                    unsigned usedb[NL];
+#pragma unroll
+                    for (int jj = 0; jj < NL; ++jj) usedb[jj] = 0u;
+                    for (int jb = 0; jb < L; jb += NL) {
+                        if ((jb & (32 * NL - 1)) == 0) {    // (a round only spans 32 * NL consecutive labels)
+#pragma unroll
+                            for (int jj = 0; jj < NL; ++jj) usedb[jj] = 0u;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < NL; ++jj) {
+                            const int j = jb + jj;
+                            if (j < L) {
+                                const int k = lab_s[j];
+                                const unsigned fr = free_s[k];
+                                const int o = off_s[k];
+                                const unsigned banks = __funnelshift_l(fr, fr, o & 31);        // free slots -> their banks
+                                const unsigned ok = banks & ~usedb[jj];
+                                const int bank = __ffs(ok ? ok : banks) - 1;
+                                const int r = (bank - o) & 31;
+                                free_s[k] = fr & ~(1u << r);
+                                usedb[jj] |= 1u << bank;
+                                slot_s[j] = o + r;
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < VCH; ++v) {
+                    const int k = lane + 32 * v;
+                    int q = koff[v];
+                    if (kcnt[v])
+                        for (int j = 0; j < L; ++j)
+                            if (lab_s[j] == k) slot_s[j] = q++;
+                }
             }
             __syncwarp();
         } else {

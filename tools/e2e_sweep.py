@@ -7,7 +7,7 @@ from bench import make_problem, T, V
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 acts, labels, al, ll = make_problem(B, 1234)
 pinned = acts.pin_memory(); grads = torch.empty((T, B, V), dtype=torch.float32, pin_memory=True)
-for nch in (1, 2, 4, 8, 16, 32):
+for nch in (8, 16, 24, 32, 48, 64, 96, 128):
     for _ in range(2): ctc_loss_host(pinned, labels, al, ll, grads_out=grads, n_chunks=nch)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(4): ctc_loss_host(pinned, labels, al, ll, grads_out=grads, n_chunks=nch)
