@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <mutex>
@@ -39,8 +40,9 @@ ctcStatus_t fail(ctcStatus_t st, const std::string &msg)
 // SP = 32*NS*W padded states; an utterance with L labels fits when SP >= 2L + 2.
 constexpr int kMaxLabelLen = 2047;           // (16, 8): SP = 4096
 constexpr int kMaxSmem = 227 * 1024;
-constexpr int kBidirMaxB = 96;              // bidirectional (two sweeps + combine) path for batches up to this size ...
-constexpr size_t kBidirMaxBytes = 192u << 20;   // ... and up to this many bytes of spilled columns
+constexpr int kBidirMaxB = 160;             // bidirectional (two sweeps + combine) path for batches up to this size ...
+constexpr size_t kBidirMaxBytes = 1u << 30;     // ... and up to this many bytes of spilled columns (B = 128, T = 1500,
+                                                // L <= 200 -- one eighth of BASELINE configs[3] -- needs 786 MB)
 constexpr int kWarpMinB = 1024;             // automatic ladder choice: warp ladder from this batch size (measured crossover,
                                             // profiles/r2_crossover.txt)
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
@@ -445,8 +447,13 @@ ctcStatus_t run(const ctcB200Call &c)
             l.v->combine<<<grid, kCombineThreads, csm, ls>>>(C);
         } else if (l.v->warp) {
             P.queue = d_queue + li; P.n_items = l.count;
-            const int grid = std::min(l.slots, persistent_grid((const void *)l.v->kernel, l.smem));
-            l.v->kernel<<<grid, 32, l.smem, ls>>>(P);
+            int smem_launch = l.smem;
+            if (const char *pad = std::getenv("CTC_B200_WARP_PAD_KB")) {          // occupancy experiments only (tools/occupancy_probe.py)
+                smem_launch = std::min(kMaxSmem, l.smem + 1024 * std::atoi(pad));
+                if (!ensure_smem_attr((const void *)l.v->kernel, smem_launch, st)) return st;
+            }
+            const int grid = std::min(l.slots, persistent_grid((const void *)l.v->kernel, smem_launch));
+            l.v->kernel<<<grid, 32, smem_launch, ls>>>(P);
             P.queue = nullptr; P.n_items = 0;
         } else {
             l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);

@@ -30,6 +30,12 @@ def _worker(rank, world, port, q):
         x = torch.tensor(acts[:, lo:hi]).cuda().requires_grad_()
         total, local = ShardedCTCLoss()(x, lab, a, l)
         local.sum().backward()
+        # the non-blocking path: engine (NO_SYNC) -> device-side cost sum -> stream-ordered NCCL all-reduce
+        from aes_lac_2018_b200.distributed import sharded_loss_step
+        t2, l2, g2, st2 = sharded_loss_step(x.detach(), lab, a, l)
+        assert t2.is_cuda and l2.is_cuda and not st2.any().item()
+        assert abs(float(t2) - float(total)) <= 1e-5 * abs(float(total)) and abs(float(l2) - float(local)) <= 1e-5 * abs(float(local))
+        assert torch.equal(g2, x.grad)
         q.put((rank, float(total), float(local), x.grad.cpu().numpy(), lo, hi))
     finally:
         dist.destroy_process_group()
