@@ -8,5 +8,5 @@ python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider --timeout 9
 python __graft_entry__.py --smoke 2>&1 | tail -3 | tee gpurun_out/smoke.log
 python bench.py 2>&1 | tail -1 | tee gpurun_out/bench_final.json
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
-    --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/bench_under_ncu.log 2>&1
+    --log-file gpurun_out/launches_final.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras --e2e-steps 1 > gpurun_out/bench_under_ncu.log 2>&1
 tail -3 gpurun_out/sanitizer.log

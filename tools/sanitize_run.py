@@ -14,12 +14,31 @@ small = synth_problem(1, 50, 5, 29, 0, 20, tmin=30)
 mid = synth_problem(2, 70, 3, 43, 40, 150 // 2, tmin=60)
 wide = synth_problem(3, 300, 1, 29, 140, 140)
 for name, prob in (("small", small), ("mid", mid), ("wide", wide)):
-    for mode, bidir in (("throughput", True), ("throughput8", True), ("latency", True), ("latency", False)):
+    for mode, bidir in (("warp", False), ("throughput", True), ("throughput8", True), ("latency", True), ("latency", False)):
         run(f"{name}/{mode}/bidir={bidir}", *prob, mode=mode, bidirectional=bidir)
     run(f"{name}/costs-only", *prob, want_grad=False)
 hostile = synth_problem(4, 120, 3, 29, 30, 60, sigma=40.0)
 run("hostile/auto", *hostile)
 run("hostile/throughput", *hostile, mode="throughput8")
+run("hostile/warp (device-side log-space detour)", *hostile, mode="warp")
+# round 2: every warp-ladder variant (NS = 2 .. 16, one and two alphabet slices), partial last chunks, blank != 0
+for L, V in ((10, 29), (40, 29), (70, 43), (100, 29), (130, 29), (170, 43), (200, 29), (250, 31)):
+    prob = synth_problem(40 + L, 2 * L + 37, 2, V, L, L, blank=3)
+    run(f"warp/L={L}/V={V}", *prob, mode="warp", blank=3)
+# round 2: non-blocking call, device-side cost sum, gradient scale, fused loss glue
+from aes_lac_2018_b200 import CTCLoss, sanitize_loss
+from aes_lac_2018_b200.ctc_loss import reduce_costs, _scale_gradients
+a, l, al, ll = small
+c_d, g_d, s_d = ctc_loss_raw(torch.tensor(a).cuda(), torch.tensor(l), torch.tensor(al), torch.tensor(ll), mode="warp", no_sync=True)
+loss, flag = reduce_costs(c_d, 0.5, True)
+_scale_gradients(g_d, 0.25, loss, flag)
+torch.cuda.synchronize()
+print("glue ok", float(loss), int(flag))
+out = torch.tensor(a).cuda().transpose(0, 1).contiguous().requires_grad_()
+ls = sanitize_loss(CTCLoss(), out, torch.tensor(l), torch.tensor(al, dtype=torch.float32) / a.shape[0], torch.tensor(ll), average=5, weight=0.7)
+ls.backward()
+torch.cuda.synchronize()
+print("sanitize_loss ok", float(ls))
 a, l, al, ll = small
 c, g, st = ctc_loss_host(torch.tensor(a).pin_memory(), torch.tensor(l), torch.tensor(al), torch.tensor(ll), n_chunks=2)
 print("host ok", float(c.sum()))
