@@ -60,6 +60,8 @@ const Variant *ladder_table(int ladder, int vch, int *n)
     case 5: return ctc_variants_group5(n);
     case 6: return ctc_variants_group6(n);
     case 7: return ctc_variants_group7(n);
+    case 8: return ctc_variants_group8(n);
+    case 9: return ctc_variants_group9(n);
     }
     *n = 0;
     return nullptr;
@@ -109,7 +111,8 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     plan.total_labels = off;
 
     // mode: 0 auto, 1 throughput ladder (16-step chunks), 2 latency ladder, 3 throughput ladder (8-step chunks),
-    // 4 warp ladder (ctc_warp.cuh: one warp per utterance, register-resident, persistent CTAs).
+    // 4 warp ladder (ctc_warp.cuh: one warp per utterance, register-resident, persistent CTAs),
+    // 5 fp32 warp ladder (ctc_warp32.cuh: the same organisation, single-precision recursion with per-lane exponents).
     // Auto (measured on B200, T=750, L~U{50..200}; profiles/): below ~2000 utterances the GPU is not full with one
     // warp per utterance, so spend more warps per utterance (latency ladder); above, the warp ladder wins.
     int vch = (V + 31) / 32;
@@ -117,12 +120,12 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 64 is not supported by this build");
     const int vch_warp = V / 32 + 1;                     // the warp ladder needs one pad lane (r = 0) after the alphabet
     if (mode == 0) mode = (B < kWarpMinB) ? 2 : 4;
-    if (mode == 4 && (vch_warp > kMaxVch || max_L > kWarpMaxLabelLen)) mode = 3;
+    if ((mode == 4 || mode == 5) && (vch_warp > kMaxVch || max_L > kWarpMaxLabelLen)) mode = 3;
     plan.latency = (mode == 2);
-    if (mode == 4) vch = vch_warp;
+    if (mode == 4 || mode == 5) vch = vch_warp;
     int nl = 0;
     const Variant *ladder = ladder_table(mode == 2 ? LADDER_LATENCY : mode == 3 ? LADDER_THROUGHPUT_K8
-                                         : mode == 4 ? LADDER_WARP : LADDER_THROUGHPUT, vch, &nl);
+                                         : mode == 4 ? LADDER_WARP : mode == 5 ? LADDER_WARP32 : LADDER_THROUGHPUT, vch, &nl);
 
     // bucket utterances by variant (counting sort: big variants first), longest first inside a bucket when the
     // lengths are ragged (tail balance).  O(B) unless T varies.
@@ -188,7 +191,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         l.slots = l.count;
         if (v->warp) {                                   // per resident CTA: 32-bit checkpoints, r images, 1/s
             l.slots = std::min(l.count, kWarpSlotCap);
-            l.ckpt_stride = want_grad ? (warp_slot_words(v->NS, v->K, v->VCH, T_max) + 1) / 2 : 0;
+            l.ckpt_stride = want_grad ? (v->slot_words(T_max) + 1) / 2 : 0;
         } else {
             l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
         }
@@ -199,7 +202,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         l.col_off = bd;  bd = align_up(bd + sizeof(unsigned) * 2 * (size_t)l.count * (size_t)T_max * v->sp(), 256);
         l.exp_off = bd;  bd = align_up(bd + sizeof(int) * 2 * (size_t)l.count * l.exp_stride, 256);
         l.z_off = bd;    bd = align_up(bd + sizeof(double) * 2 * (size_t)l.count * 4, 256);
-        l.smem = v->warp ? make_warp_layout(v->NS, v->K, v->VCH, v->warp == 2).total : make_layout(v->NS, v->W, v->K, V, T_max).total;
+        l.smem = v->smem_bytes(V, T_max);
         if (l.smem > kMaxSmem)
             return fail(CTC_STATUS_UNKNOWN_ERROR,
                         "alphabet_size / max_time too large for the shared-memory layout of this kernel");
@@ -356,7 +359,7 @@ ctcStatus_t run(const ctcB200Call &c)
         return fail(CTC_STATUS_INVALID_VALUE, "non-positive size");
     if (c.blank_label < 0 || c.blank_label >= c.alphabet_size)
         return fail(CTC_STATUS_INVALID_VALUE, "blank_label outside the alphabet");
-    if (c.flags & ~0x70fu) return fail(CTC_STATUS_INVALID_VALUE, "unknown bits in flags");
+    if ((c.flags & ~0x70fu) || ((c.flags >> 8) & 0x7) > 5) return fail(CTC_STATUS_INVALID_VALUE, "unknown bits in flags");
     const bool no_sync = (c.flags & CTC_B200_FLAG_NO_SYNC) != 0;
     if (no_sync && (c.costs_host || c.status_host))
         return fail(CTC_STATUS_INVALID_VALUE, "NO_SYNC cannot return host costs/status");
@@ -711,7 +714,7 @@ ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_l
     if (!size_bytes) return fail(CTC_STATUS_INVALID_VALUE, "null size_bytes");
     // take the max over the ladders so that a forced mode never overruns the workspace
     size_t need = 0;
-    for (int mode = 1; mode <= 4; ++mode) {
+    for (int mode = 1; mode <= 5; ++mode) {
         thread_local Plan p;
         ctcStatus_t st = make_plan(label_lengths, input_lengths, alphabet_size, minibatch, max_time,
                                    want_gradients != 0, mode, p, /*size_only=*/true);

@@ -1,8 +1,8 @@
-// ctc_variants.cu -- instantiates one group of kernel variants (compile with -DCTC_GROUP=0..5).
+// ctc_variants.cu -- instantiates one group of kernel variants (compile with -DCTC_GROUP=0..9).
 #include "ctc_variants.h"
 
 #ifndef CTC_GROUP
-#error "compile with -DCTC_GROUP=<0..7>"
+#error "compile with -DCTC_GROUP=<0..9>"
 #endif
 
 namespace ctcb200 {
@@ -14,6 +14,8 @@ namespace ctcb200 {
 #elif CTC_GROUP / 2 == 3
 #define VW_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp_kernel<NS, K, CTC_VCH, MAXR, 0>, nullptr, 1}
 #define VWS_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp_kernel<NS, K, CTC_VCH, MAXR, 1>, nullptr, 2}
+#elif CTC_GROUP / 2 == 4
+#define VF_(NS, K, MAXR) Variant{NS, 1, K, CTC_VCH, ctc_warp32_kernel<NS, K, CTC_VCH, MAXR>, nullptr, 3}
 #else
 #define V_(NS, W, K) Variant{NS, W, K, CTC_VCH, ctc_fused_kernel<NS, W, K, CTC_VCH>, nullptr, 0}
 #endif
@@ -34,6 +36,13 @@ static const Variant kTable[] = {
 #else
     // (measured per label-length class on B200, profiles/r2_variant_matrix.txt)
     VW_(2, 16, 128), VW_(4, 8, 128), VW_(6, 8, 168), VW_(8, 8, 168), VWS_(10, 8, 144), VWS_(12, 8, 168), VW_(14, 8, 232), VW_(16, 8, 255),
+#endif
+#elif CTC_LADDER == 4
+    // one warp per utterance, fp32 recursion with per-lane block exponents (ctc_warp32.cuh): (NS, K, register cap)
+#ifdef CTC_WARP32_TABLE_INC        // kernel experiments: the table comes from a file (tools/build_alt.sh)
+#include CTC_WARP32_TABLE_INC
+#else
+    VF_(2, 8, 96), VF_(4, 8, 96), VF_(6, 8, 128), VF_(8, 8, 128), VF_(10, 8, 128), VF_(12, 8, 168), VF_(14, 8, 168), VF_(16, 8, 168),
 #endif
 #else
     // latency: more warps per utterance, fewer states per thread

@@ -45,7 +45,7 @@ constexpr int kWarpTargetExp = 192;     // column max after a rescale: 2^192 (he
 constexpr unsigned kFull = 0xffffffffu;
 
 struct WarpLayout {
-    int PS;                              // product row stride (floats); slot PS-1 is the dump slot of padding labels
+    int PS;                              // product row stride (floats); the last 32 slots are per-lane dump slots of padding labels
     int off_prod, off_lab, off_slot, off_cnt, off_off, off_av, off_stg, total;
 };
 
@@ -54,7 +54,7 @@ __host__ __device__ inline WarpLayout make_warp_layout(int NS, int K, int VCH, i
 {
     WarpLayout l;
     const int LP = 16 * NS;
-    l.PS = LP + 64;
+    l.PS = LP + 96;                     // labels + segment padding (< 64) + one dump slot per lane
     int o = 0;
     l.off_prod = o;                      // [K][PS] floats: alpha*tb products of a chunk, grouped by symbol
     l.off_lab = o;                       // [LP] ints   (prologue only: aliases the product rows)
@@ -294,7 +294,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
                     }
                     off_s[k] = o;
                 }
-                if (cur > PS - 1) {                         // padded segments do not fit: plain prefix sums (bank conflicts, same result)
+                if (cur > PS - 32) {                        // padded segments do not fit: plain prefix sums (bank conflicts, same result)
                     int o = 0;
                     for (int k = 0; k < 32 * VCH; ++k) { off_s[k] = o; o += cnt_s[k]; }
                 }
@@ -364,7 +364,8 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
 #pragma unroll
         for (int jj = 0; jj < NL; ++jj) {
             const int j = j0 + jj;
-            sl[jj] = (want_grad && j < L) ? slot_s[j] : PS - 1;
+            sl[jj] = (want_grad && j < L) ? slot_s[j] : PS - 32 + lane;   // (a shared dump slot is a benign write-write race,
+                                                                          //  but racecheck rightly reports it)
         }
         __syncwarp();
 

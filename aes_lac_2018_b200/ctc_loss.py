@@ -140,7 +140,7 @@ def ctc_loss_raw(acts: torch.Tensor, labels, act_lens, label_lens, blank: int = 
         kms = ctypes.c_float(0.0)
         call.kernel_ms_host = ctypes.cast(ctypes.pointer(kms), ctypes.c_void_p) if timing is not None else None
         call.flags = {"auto": 0, "throughput": _lib.FLAG_MODE_THROUGHPUT, "latency": _lib.FLAG_MODE_LATENCY,
-                      "throughput8": _lib.FLAG_MODE_THROUGHPUT_K8, "warp": _lib.FLAG_MODE_WARP}[mode]
+                      "throughput8": _lib.FLAG_MODE_THROUGHPUT_K8, "warp": _lib.FLAG_MODE_WARP, "warp32": _lib.FLAG_MODE_WARP32}[mode]
         if serial_launches:
             call.flags |= _lib.FLAG_SERIAL_LAUNCHES
         if not bidirectional:

@@ -121,7 +121,8 @@ ctcStatus_t get_workspace_size(const int *const label_lengths,
 #define CTC_B200_FLAG_NO_BIDIR 0x8u        /* small batches: keep the three-sweep fused kernel instead of the bidirectional path */
 #define CTC_B200_FLAG_NO_FALLBACK 0x4u     /* report out-of-range utterances instead of re-running them in log space */
 /* bits 8..10: variant ladder override (0 auto, 1 throughput, 2 latency, 3 throughput with 8-step chunks,
- * 4 warp ladder: one warp per utterance, register-resident -- the large-batch default) */
+ * 4 warp ladder: one warp per utterance, register-resident, fp64 recursion;
+ * 5 fp32 warp ladder: the same organisation with a single-precision recursion and per-lane block exponents) */
 
 typedef struct ctcB200Call {
     const float *activations;   /* DEVICE; element (t,b,k) at t*act_stride_t + b*act_stride_b + k */

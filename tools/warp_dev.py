@@ -11,7 +11,7 @@ import torch
 from aes_lac_2018_b200 import ctc_loss_raw
 
 
-def parity():
+def parity(pmodes=("warp",)):
     from oracle import ctc_f64
     from tests.helpers import synth_problem
     cases = {
@@ -32,7 +32,7 @@ def parity():
     for name, kw in cases.items():
         acts, labels, al, ll = synth_problem(**kw)
         oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
-        for mode in ("warp",):
+        for mode in pmodes:
             try:
                 c, g, st = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll),
                                         mode=mode)
@@ -51,11 +51,11 @@ def parity():
     # blank != 0 and forward only
     acts, labels, al, ll = synth_problem(seed=31, T=120, B=6, V=29, lmin=5, lmax=40, blank=5)
     oc, og = ctc_f64.ctc_batch(acts, labels, al, ll, blank=5)
-    c, g, st = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), blank=5, mode="warp")
+    c, g, st = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), blank=5, mode=pmodes[0])
     d = np.abs(g.cpu().numpy() - og).max()
     print(f"blank5: loss rel {np.abs(c.numpy() - oc).max():.2e} grad {d:.2e}")
     ok &= d <= 1e-5
-    c2, _, _ = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), blank=5, mode="warp",
+    c2, _, _ = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), blank=5, mode=pmodes[0],
                             want_grad=False)
     print("forward-only equal:", bool((c2 == c).all()))
     return ok
@@ -88,10 +88,13 @@ def timing(modes):
 
 if __name__ == "__main__":
     modes = ["warp", "throughput8"]
+    pmodes = ["warp"]
     for a in sys.argv[1:]:
         if a.startswith("--modes"):
             modes = a.split("=")[1].split(",")
+        if a.startswith("--pmodes"):
+            pmodes = a.split("=")[1].split(",")
     t0 = time.time()
     if "--no-parity" not in sys.argv:
-        print("parity ok" if parity() else "PARITY FAILED", f"({time.time() - t0:.0f} s)")
+        print("parity ok" if parity(pmodes) else "PARITY FAILED", f"({time.time() - t0:.0f} s)")
     timing(modes)
