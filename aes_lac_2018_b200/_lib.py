@@ -20,7 +20,7 @@ FLAG_MODE_THROUGHPUT_K8 = 3 << 8
 FLAG_MODE_WARP = 4 << 8
 FLAG_MODE_WARP32 = 5 << 8
 
-UTT_INFEASIBLE, UTT_INF_COST, UTT_BAD_LABEL, UTT_RANGE, UTT_LOGSPACE = 1, 2, 4, 8, 16
+UTT_INFEASIBLE, UTT_INF_COST, UTT_BAD_LABEL, UTT_RANGE, UTT_LOGSPACE, UTT_WIDE = 1, 2, 4, 8, 16, 32
 
 
 class _OptUnion(ctypes.Union):

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
@@ -47,7 +48,7 @@ constexpr int kWarpMinB = 1024;             // automatic ladder choice: warp lad
                                             // profiles/r2_crossover.txt)
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
 constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)
-constexpr int kMaxLaunches = 16;
+constexpr int kMaxLaunches = 32;            // queue counters: launches of one call (fp32 ladder: first and second tier)
 
 const Variant *ladder_table(int ladder, int vch, int *n)
 {
@@ -73,15 +74,21 @@ struct Plan {
     int B = 0, T_max = 0, V = 0;
     bool latency = false;
     std::vector<int> meta;                   // [label_off B | label_len B | act_len B | utt_ids B]
-    struct Launch { const Variant *v; int first, count; size_t ckpt_off; long long ckpt_stride; int smem;
+    struct Launch { const Variant *v; const Variant *v2 = nullptr;       // v2: fp64 second tier behind an fp32 warp variant
+                    int first, count; size_t ckpt_off; long long ckpt_stride; int smem, smem2 = 0;
                     size_t col_off, exp_off, z_off; int exp_stride;      // bidirectional path (column spill) offsets
-                    int slots; };                                        // warp ladder: workspace slots (= max persistent CTAs)
+                    int slots;                                           // warp ladder: workspace slots (= max persistent CTAs)
+                    long long frames = 0;                                // sum of the input lengths of the bucket
+                    int sm_lo = 0, sm_hi = 0; };                         // warp ladders, several buckets: SM range of this one
     bool bidir = false;
     std::vector<Launch> launches;
     long long total_labels = 0;
     size_t off_meta = 0, off_labels = 0, off_costs = 0, off_status = 0, off_queue = 0, off_ckpt = 0, total = 0, ckpt_bytes = 0;
     int fallback_S = 1;
 };
+
+int persistent_grid(const void *kernel, int smem);
+double warp_rel_cost(const Variant *v);
 
 // forced_w: 0 = automatic ladder choice; otherwise use the latency ladder entry with that W where possible
 ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V, int B, int T_max,
@@ -132,6 +139,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     thread_local std::vector<int> cls, cls_of_len;       // scratch reused across calls (a fresh 32 KB+ vector per call
     cls.resize(B);                                       //  costs more than the whole pass: mmap / page faults)
     std::vector<int> count(nl, 0);
+    std::vector<long long> frames(nl, 0);
     int t_min = 0x7fffffff, t_max = 0;
     // Small batches (bidirectional path): one variant for everybody -- the per-step latency of the latency ladder
     // barely depends on the variant, while every extra bucket costs two more launches and a stream fork/join.
@@ -150,6 +158,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     for (int b = 0; b < B; ++b) {
         cls[b] = cls_of_len[one_bucket ? max_L : label_len[b]];
         ++count[cls[b]];
+        frames[cls[b]] += act_len[b];
         t_min = std::min(t_min, act_len[b]);
         t_max = std::max(t_max, act_len[b]);
     }
@@ -177,7 +186,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     plan.off_labels = o; o = align_up(o + sizeof(int) * (size_t)std::max<long long>(off, 1), 256);
     plan.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
     plan.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
-    plan.off_queue = o;  o = align_up(o + sizeof(int) * (kMaxLaunches + 1), 256);   // (+1: the log-space detour)
+    plan.off_queue = o;  o = align_up(o + sizeof(int) * 4 * (kMaxLaunches + 1), 256);   // per launch (+1: the log-space detour): work queue, retired CTAs, claimed slots
     plan.off_ckpt = o;
     size_t ck = 0, bd = 0;
     plan.bidir = one_bucket;
@@ -185,18 +194,26 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         if (count[c] == 0) continue;
         const Variant *v = &ladder[c];
         Plan::Launch l;
-        l.v = v; l.first = start[c]; l.count = count[c];
+        l.v = v; l.first = start[c]; l.count = count[c]; l.frames = frames[c];
         const int nC = (T_max + v->K - 1) / v->K;
         // per CTA: nC checkpoint columns (SP doubles each) followed by nC p~ images
         l.slots = l.count;
         if (v->warp) {                                   // per resident CTA: 32-bit checkpoints, r images, 1/s
             l.slots = std::min(l.count, kWarpSlotCap);
-            l.ckpt_stride = want_grad ? (v->slot_words(T_max) + 1) / 2 : 0;
+            long long words = v->slot_words(T_max);
+            if (v->warp == 3) {                          // second tier: the fp64 warp variant of the same NS shares the slots
+                int n2 = 0;
+                const Variant *t2 = ladder_table(LADDER_WARP, vch, &n2);
+                for (int i = 0; i < n2; ++i)
+                    if (t2[i].NS == v->NS) l.v2 = &t2[i];
+                if (!l.v2) return fail(CTC_STATUS_UNKNOWN_ERROR, "no fp64 second-tier variant for this label length");
+                words = std::max(words, l.v2->slot_words(T_max));
+                l.smem2 = l.v2->smem_bytes(V, T_max);
+            }
+            l.ckpt_stride = want_grad ? (words + 1) / 2 : 0;
         } else {
             l.ckpt_stride = want_grad ? (long long)nC * v->sp() + (long long)nC * (pimg_bytes(v->K, V) / 8) : 0;
         }
-        l.ckpt_off = ck;
-        ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.slots;
         // bidirectional path: 2 slots (forward, reversed) of T_max columns of SP high words, exponents, Z
         l.exp_stride = nC + 2;
         l.col_off = bd;  bd = align_up(bd + sizeof(unsigned) * 2 * (size_t)l.count * (size_t)T_max * v->sp(), 256);
@@ -208,6 +225,40 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
                         "alphabet_size / max_time too large for the shared-memory layout of this kernel");
         if (plan.bidir && (!v->combine || combine_smem_bytes(v->sp(), V) > kMaxSmem)) plan.bidir = false;
         plan.launches.push_back(l);
+    }
+    // Warp ladders: workspace slots are per RESIDENT CTA.  Several buckets in one call: every bucket gets a contiguous
+    // range of SMs in proportion to its share of the work, so that all buckets run side by side from the start and
+    // finish together (outside_sm_range() in ctc_fused.cuh).  Full-size grids without ranges fill the SMs in launch
+    // order: the later buckets only start as earlier CTAs retire and the call ends with a long, half-empty tail
+    // (12-16 % below the per-class throughputs); smaller grids that share SMs thrash the instruction cache (2x slower).
+    if (!plan.launches.empty() && plan.launches[0].v->warp) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        const int n = (int)plan.launches.size();
+        const bool ranges = n > 1 && n <= sms && !std::getenv("CTC_B200_FULL_GRIDS");
+        double tot = 0.0, acc = 0.0;
+        for (const Plan::Launch &l : plan.launches) tot += (double)std::max<long long>(l.frames, 1) * warp_rel_cost(l.v);
+        int cut = 0;
+        for (int i = 0; i < n; ++i) {
+            Plan::Launch &l = plan.launches[i];
+            const int per_sm = std::max(1, persistent_grid((const void *)l.v->kernel, l.smem) / sms);
+            if (ranges) {
+                acc += (double)std::max<long long>(l.frames, 1) * warp_rel_cost(l.v);
+                int next = (i == n - 1) ? sms : (int)std::lround(sms * acc / tot);
+                next = std::max(next, cut + 1);                     // at least one SM each ...
+                next = std::min(next, sms - (n - 1 - i));           // ... and room for the buckets still to come
+                l.sm_lo = cut; l.sm_hi = next;
+                cut = next;
+                l.slots = std::min(l.count, per_sm * (l.sm_hi - l.sm_lo) + 1);
+            } else {
+                l.slots = std::min(l.count, per_sm * sms);
+            }
+        }
+    }
+    for (Plan::Launch &l : plan.launches) {
+        l.ckpt_off = ck;
+        ck += sizeof(double) * (size_t)l.ckpt_stride * (size_t)l.slots;
     }
     if (plan.bidir) ck = std::max(ck, bd);
     // the checkpoint area doubles as the alpha store of the log-space fallback: keep room for one utterance
@@ -296,6 +347,10 @@ bool ensure_smem_attr(const void *kernel, int smem, ctcStatus_t &st)
         }
     if (!check(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem),
                "cudaFuncSetAttribute(smem)", CTC_STATUS_EXECUTION_FAILED, st)) return false;
+    // (experiment: one shared-memory carve-out for every kernel -- measured slightly slower than the driver's choice)
+    if (std::getenv("CTC_B200_MAX_CARVEOUT") &&
+        !check(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+               "cudaFuncSetAttribute(carveout)", CTC_STATUS_EXECUTION_FAILED, st)) return false;
     done.push_back(Key{kernel, dev, smem});
     return true;
 }
@@ -315,6 +370,17 @@ int persistent_grid(const void *kernel, int smem)
     const int grid = std::max(1, per_sm) * std::max(1, sms);
     done.push_back(Key{kernel, dev, smem, grid});
     return grid;
+}
+
+// Relative cost of one utterance-frame per warp-ladder variant (measured per label class on B200 at B = 8192, T = 750:
+// profiles/r2_variant_matrix.txt, profiles/r2_w32_variants.txt).  Only the ratios matter: they size the persistent
+// grids of the buckets of one call so that all buckets finish together (below).
+double warp_rel_cost(const Variant *v)
+{
+    static const double c64[9] = {0, 1.20, 1.44, 1.80, 2.21, 2.70, 3.28, 3.80, 4.33};   // NS = 2 .. 16, fp64 recursion
+    static const double c32[9] = {0, 1.05, 1.27, 1.55, 1.77, 2.01, 2.43, 2.70, 3.03};   // fp32 recursion
+    const int i = std::max(1, std::min(v->NS / 2, 8));
+    return v->warp == 3 ? c32[i] : c64[i];
 }
 
 // Enqueue the device-side log-space detour behind the fast kernels of this call (ctc_logspace.cuh): persistent CTAs
@@ -396,10 +462,10 @@ ctcStatus_t run(const ctcB200Call &c)
     P.V = V; P.T_max = c.max_time; P.B = B; P.blank = c.blank_label;
     P.grad_scale = c.grad_scale;
     P.debug = c.debug_device;
-    P.queue = nullptr; P.n_items = 0;
+    P.queue = nullptr; P.n_items = 0; P.only_flagged = 0; P.sm_lo = 0; P.sm_hi = 0; P.n_slots = 0;
     int *d_queue = (int *)(ws + plan.off_queue);
-    if ((int)plan.launches.size() > kMaxLaunches) return fail(CTC_STATUS_UNKNOWN_ERROR, "too many kernel variants in one call");
-    if (!check(cudaMemsetAsync(d_queue, 0, sizeof(int) * (kMaxLaunches + 1), stream), "queue memset", CTC_STATUS_MEMOPS_FAILED, st))
+    if ((int)plan.launches.size() > kMaxLaunches / 2) return fail(CTC_STATUS_UNKNOWN_ERROR, "too many kernel variants in one call");
+    if (!check(cudaMemsetAsync(d_queue, 0, sizeof(int) * 4 * (kMaxLaunches + 1), stream), "queue memset", CTC_STATUS_MEMOPS_FAILED, st))
         return st;
 
     const bool serial = (c.flags & CTC_B200_FLAG_SERIAL_LAUNCHES) != 0;
@@ -449,15 +515,31 @@ ctcStatus_t run(const ctcB200Call &c)
             dim3 grid((c.max_time + C.frames_per_cta - 1) / C.frames_per_cta, l.count);
             l.v->combine<<<grid, kCombineThreads, csm, ls>>>(C);
         } else if (l.v->warp) {
-            P.queue = d_queue + li; P.n_items = l.count;
+            P.n_items = l.count;
             int smem_launch = l.smem;
             if (const char *pad = std::getenv("CTC_B200_WARP_PAD_KB")) {          // occupancy experiments only (tools/occupancy_probe.py)
                 smem_launch = std::min(kMaxSmem, l.smem + 1024 * std::atoi(pad));
                 if (!ensure_smem_attr((const void *)l.v->kernel, smem_launch, st)) return st;
             }
-            const int grid = std::min(l.slots, persistent_grid((const void *)l.v->kernel, smem_launch));
+            // with an SM range the grid is full-size (CTAs outside the range retire at once, the others claim a slot)
+            const int full = persistent_grid((const void *)l.v->kernel, smem_launch);
+            const int grid = (l.sm_hi > l.sm_lo) ? full : std::min(l.slots, full);
+            P.sm_lo = l.sm_lo; P.sm_hi = l.sm_hi; P.n_slots = l.slots;
+            P.queue = d_queue + 4 * li;
             l.v->kernel<<<grid, 32, smem_launch, ls>>>(P);
-            P.queue = nullptr; P.n_items = 0;
+            if (l.v2 && !(c.flags & CTC_B200_FLAG_NO_FALLBACK)) {
+                // fp32 kernel: utterances that failed its range self-check are redone by the fp64 kernel of the same
+                // label class, which scans the status words of the bucket (nothing flagged: a few microseconds)
+                if (!check(cudaGetLastError(), "kernel launch", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+                if (!ensure_smem_attr((const void *)l.v2->kernel, l.smem2, st)) return st;
+                P.queue = d_queue + 4 * (kMaxLaunches / 2 + li); P.only_flagged = 1;
+                const int full2 = persistent_grid((const void *)l.v2->kernel, l.smem2);
+                const int grid2 = (l.sm_hi > l.sm_lo) ? full2 : std::min(l.slots, full2);
+                l.v2->kernel<<<grid2, 32, l.smem2, ls>>>(P);
+                P.only_flagged = 0;
+                ++g_launches;
+            }
+            P.queue = nullptr; P.n_items = 0; P.sm_lo = 0; P.sm_hi = 0;
         } else {
             l.v->kernel<<<l.count, 32 * l.v->W, l.smem, ls>>>(P);
         }
@@ -473,7 +555,7 @@ ctcStatus_t run(const ctcB200Call &c)
     // cost) are redone in log space by a kernel that finds them itself: no host round trip, so NO_SYNC calls get
     // the detour too.
     if (!(c.flags & CTC_B200_FLAG_NO_FALLBACK)) {
-        st = launch_logspace_detour(c, plan, P, d_queue + kMaxLaunches, stream);
+        st = launch_logspace_detour(c, plan, P, d_queue + 4 * kMaxLaunches, stream);
         if (st != CTC_STATUS_SUCCESS) return st;
     }
     if (tim && !check(cudaEventRecord(tim->t1, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;

@@ -59,6 +59,7 @@ enum : int {
     UTT_BAD_LABEL = 0x4,
     UTT_RANGE = 0x8,
     UTT_LOGSPACE = 0x10,
+    UTT_WIDE = 0x20,
 };
 
 struct FusedParams {
@@ -86,8 +87,13 @@ struct FusedParams {
     int col_exp_stride;
     double *col_z;                    // [gridDim.x][4]: Z^, Ea_fin, log Z (natural), unused
     // --- one-warp-per-utterance kernel (ctc_warp.cuh): persistent CTAs pulling utterances from a queue ---
-    int *queue;                       // work counter (zeroed before the launch), or nullptr: CTA i does item i
+    int *queue;                       // [0] work counter, [1] retired CTAs, [2] claimed workspace slots (zeroed before the
+                                      // launch), or nullptr: CTA i does item i
     int n_items;                      // utterances of this launch
+    int sm_lo, sm_hi;                 // several buckets in one call: this launch keeps to the SMs [sm_lo, sm_hi) (0, 0: all)
+    int n_slots;                      // ... its CTAs claim one of n_slots workspace slots (queue[2]) instead of using blockIdx.x
+    int only_flagged;                 // ctc_warp_kernel as the second tier behind ctc_warp32_kernel: redo only the utterances
+                                      // whose status says RANGE / INF_COST (fp64 range), skip everything else
 };
 
 // ---- shared-memory carve-up (host and device must agree) ---------------------------------------
@@ -146,6 +152,31 @@ __host__ __device__ inline SmemLayout make_layout(int NS, int W, int K, int V, i
 }
 
 // ---- small device helpers ------------------------------------------------------------------------
+// Persistent warp kernels, several label classes in one call: each class is given a contiguous range of SMs in
+// proportion to its work, so that the classes run side by side from start to end without sharing an SM (six
+// different 20 KB loop bodies on one SM thrash the 32 KB instruction cache: measured 2x slower).  The grid is
+// launched full-size; a CTA that lands outside its range retires at once -- unless it is the last CTA of the grid
+// and work is left (never observed; it keeps the scheme correct whatever the block scheduler does).
+// Returns true if this CTA must retire.
+__device__ __forceinline__ bool outside_sm_range(int sm_lo, int sm_hi, int *queue, int n_slots, int &slot)
+{
+    slot = (int)blockIdx.x;
+    if (sm_hi <= sm_lo) return false;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    int stay = ((int)smid >= sm_lo && (int)smid < sm_hi);
+    int s = 0;
+    if ((threadIdx.x & 31) == 0) {
+        if (!stay) stay = (atomicAdd(queue + 1, 1) == (int)gridDim.x - 1);     // last one out: drain what is left
+        if (stay) {
+            s = atomicAdd(queue + 2, 1);
+            if (s >= n_slots) { stay = 0; atomicAdd(queue + 1, 1); }            // more resident CTAs than the plan assumed
+        }
+    }
+    stay = __shfl_sync(0xffffffffu, stay, 0);
+    slot = __shfl_sync(0xffffffffu, s, 0);
+    return !stay;
+}
 __device__ __forceinline__ double pow2d(int e)            // 2^e, e in [-1022, 1023]
 {
     return __hiloint2double((e + 1023) << 20, 0);

@@ -189,7 +189,9 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
     const long long gst = (long long)P.B * V;               // gradient row stride (dense)
     const bool want_grad = (P.grads != nullptr);
     const int nCmax = warp_max_chunks(K, P.T_max);
-    unsigned *ckw = (unsigned *)P.ckpt + (long long)blockIdx.x * (P.ckpt_stride * 2);   // [nCmax][NS][32] checkpoint high words
+    int slot;
+    if (outside_sm_range(P.sm_lo, P.sm_hi, P.queue, P.n_slots, slot)) return;
+    unsigned *ckw = (unsigned *)P.ckpt + (long long)slot * (P.ckpt_stride * 2);   // [nCmax][NS][32] checkpoint high words
     int *eaw = (int *)(ckw + (long long)nCmax * SP);                                // [nCmax] alpha exponent of the chunk
     unsigned *imgw = (unsigned *)(eaw + ((nCmax + 31) & ~31));                      // [T_max][VCH][32] r high words
     float *invw = (float *)(imgw + (long long)P.T_max * VCH * 32);                  // [T_max] 1 / s_t
@@ -214,6 +216,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         }
         if (item >= P.n_items) break;
         const int b = P.utt_ids[item];
+        if (P.only_flagged && !(P.status[b] & (UTT_RANGE | UTT_INF_COST))) continue;    // second tier: flagged utterances only
         long long dbg_c0 = 0, dbg_n0 = 0, dbg_c1 = 0;
         if (P.debug && lane == 0) {
             dbg_c0 = clock64();
@@ -241,10 +244,10 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         rep = __reduce_add_sync(kFull, rep);
         bad = __any_sync(kFull, bad);
         __syncwarp();
-        int ustat = 0;
+        int ustat = P.only_flagged ? UTT_WIDE : 0;
         if (bad) ustat |= UTT_BAD_LABEL;
         if (T <= 0 || L + rep > T) ustat |= UTT_INFEASIBLE;
-        if (ustat) {                                        // cost 0, gradient 0 (warp-ctc CPU convention)
+        if (ustat & (UTT_BAD_LABEL | UTT_INFEASIBLE)) {     // cost 0, gradient 0 (warp-ctc CPU convention)
             if (lane == 0) { P.costs[b] = 0.f; P.status[b] = ustat; }
             if (want_grad)
                 for (int t = 0; t < P.T_max; ++t)
@@ -725,6 +728,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
             for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
         dbg_out();
     }
+    if (P.sm_hi > P.sm_lo && lane == 0) atomicAdd(P.queue + 1, 1);
 }
 
 }  // namespace ctcb200

@@ -82,15 +82,22 @@ __host__ __device__ inline long long warp32_slot_words(int NS, int K, int VCH, i
 
 __device__ __forceinline__ float exp2i(int n) { return __int_as_float((n + 127) << 23); }   // 2^n, n in [-126, 127]
 
-// x[] *= 2^d (d clamped to +-252; two exact factors)
+// x[] *= 2^d (d clamped to +-252).  One exact factor when every lane's |d| <= 126 (warp-uniform test: almost always),
+// two otherwise.
 template <int NS>
 __device__ __forceinline__ void scale32(float (&x)[NS], int d)
 {
     d = max(-252, min(d, 252));
-    const int h = d >> 1;
-    const float f1 = exp2i(h), f2 = exp2i(d - h);
+    if (__all_sync(kFull, (unsigned)(d + 126) <= 252u)) {
+        const float f = exp2i(d);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) x[i] = (x[i] * f1) * f2;
+        for (int i = 0; i < NS; ++i) x[i] *= f;
+    } else {
+        const int h = d >> 1;
+        const float f1 = exp2i(h), f2 = exp2i(d - h);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) x[i] = (x[i] * f1) * f2;
+    }
 }
 
 // Per-lane block exponent for the next chunk.  UP: mass flows towards higher lanes (alpha), else towards lower (beta).
@@ -149,7 +156,9 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
     const long long gst = (long long)P.B * V;               // gradient row stride (dense)
     const bool want_grad = (P.grads != nullptr);
     const int nCmax = warp_max_chunks(K, P.T_max);
-    float *ckw = (float *)P.ckpt + (long long)blockIdx.x * (P.ckpt_stride * 2);     // [nCmax][NS + 1][32] column, exponents
+    int slot;
+    if (outside_sm_range(P.sm_lo, P.sm_hi, P.queue, P.n_slots, slot)) return;
+    float *ckw = (float *)P.ckpt + (long long)slot * (P.ckpt_stride * 2);     // [nCmax][NS + 1][32] column, exponents
     float *imgw = ckw + (long long)nCmax * CW;                                      // [T_max][VCH][32] p~
     float *invw = imgw + (long long)P.T_max * VCH * 32;                             // [T_max] 1 / s_t
     const int bl = blank & 31, bs = blank >> 5;
@@ -581,28 +590,32 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             }
 
             // -- gather: lane k sums the products of symbol k for the KK frames of the chunk --
-            float gsum[KK];
-#pragma unroll
-            for (int tt = 0; tt < KK; ++tt) gsum[tt] = 0.f;
-            float *grow = grads_b + (long long)t0 * gst + lane;
+            float acc[VCH][KK];
 #pragma unroll
             for (int v = 0; v < VCH; ++v) {
-                float acc[KK];
 #pragma unroll
-                for (int tt = 0; tt < KK; ++tt) acc[tt] = 0.f;
+                for (int tt = 0; tt < KK; ++tt) acc[v][tt] = 0.f;
                 const float *gp = prod + koff[v];
                 for (int qq = 0; qq < kcnt[v]; ++qq) {
 #pragma unroll
-                    for (int tt = 0; tt < KK; ++tt) acc[tt] += gp[tt * PS + qq];
+                    for (int tt = 0; tt < KK; ++tt) acc[v][tt] += gp[tt * PS + qq];
                 }
+            }
+            // gradient rows: lane = symbol (coalesced)
+            float gsum[KK];
+            float *grow = grads_b + (long long)t0 * gst + lane;
+            const float nscale = -scale * P.grad_scale;
 #pragma unroll
-                for (int tt = 0; tt < KK; ++tt) {
-                    pmax = max(pmax, __float_as_uint(acc[tt]));
-                    const float inv_t = __shfl_sync(kFull, myinv, tt);
-                    const float g = wr[v] ? fmaf(rcur[tt][v], inv_t, -acc[tt] * scale) * P.grad_scale : 0.f;
-                    if (wr[v]) grow[tt * gst + 32 * v] = g;
-                    gsum[tt] += g;
+            for (int tt = 0; tt < KK; ++tt) {
+                const float inv_t = __shfl_sync(kFull, myinv, tt) * P.grad_scale;
+                gsum[tt] = 0.f;
+#pragma unroll
+                for (int v = 0; v < VCH; ++v) {
+                    pmax = max(pmax, __float_as_uint(acc[v][tt]));
+                    const float g = fmaf(rcur[tt][v], inv_t, acc[v][tt] * nscale);
+                    if (wr[v]) { grow[32 * v] = g; gsum[tt] += g; }
                 }
+                grow += gst;
             }
             // the blank entry of frame tt is minus the sum of the row's other entries; written by lane tt
             const float total = warp_sum_transposed<KK>(gsum, lane);
@@ -631,10 +644,17 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
         if (!(chk_dev <= kCheckTol) || pmax > 0x40100000u) ustat |= UTT_RANGE;   // (acc = posterior * mz * q < 2; NaN / inf land here)
         if (__any_sync(kFull, ustat & UTT_RANGE)) ustat |= UTT_RANGE;
         if (lane == 0) P.status[b] = ustat;
+        if (P.debug && lane == 0) {                         // development aid: what the self-checks saw
+            P.debug[b * 16 + 0] = __float_as_uint(chk_dev);
+            P.debug[b * 16 + 1] = pmax;
+            P.debug[b * 16 + 2] = hmax;
+            P.debug[b * 16 + 3] = ustat;
+        }
         // padded frames get zero gradient
         for (int t = T; t < P.T_max; ++t)
             for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
     }
+    if (P.sm_hi > P.sm_lo && lane == 0) atomicAdd(P.queue + 1, 1);
 }
 
 }  // namespace ctcb200

@@ -160,6 +160,8 @@ typedef struct ctcB200Call {
                                            with the fallback disabled */
 #define CTC_B200_UTT_LOGSPACE 0x10      /* the utterance exceeded the fp64 linear-domain range of the fused kernel
                                            (or has a +inf cost) and was computed by the fp64 log-space kernel */
+#define CTC_B200_UTT_WIDE 0x20          /* informational: the utterance exceeded the range of the fp32 kernel (per-lane block
+                                           exponents) and was computed by the fp64 linear-domain kernel */
 
 ctcStatus_t ctc_b200_workspace_size(const int *label_lengths, const int *input_lengths,
                                     int alphabet_size, int minibatch, int max_time,

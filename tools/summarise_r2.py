@@ -110,6 +110,8 @@ def kernel(rep, name, B, T, what):
     for op, c in ops.most_common(22):
         out.append(f"  {op:12s} {c / steps:7.2f}   {100 * smp[op] / max(1, tots):5.1f} %")
     path = os.path.join(ROOT, "profiles", f"r2_ncu_{name}.txt")
+    if os.environ.get("SUMMARY_OUT"):
+        path = os.environ["SUMMARY_OUT"]
     open(path, "w").write("\n".join(out) + "\n")
     print("\n".join(out))
 
