@@ -126,7 +126,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     if (vch > kMaxVch)
         return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 64 is not supported by this build");
     const int vch_warp = V / 32 + 1;                     // the warp ladder needs one pad lane (r = 0) after the alphabet
-    if (mode == 0) mode = (B < kWarpMinB) ? 2 : 4;
+    if (mode == 0) mode = (B < kWarpMinB) ? 2 : 5;
     if ((mode == 4 || mode == 5) && (vch_warp > kMaxVch || max_L > kWarpMaxLabelLen)) mode = 3;
     plan.latency = (mode == 2);
     if (mode == 4 || mode == 5) vch = vch_warp;
@@ -201,7 +201,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         if (v->warp) {                                   // per resident CTA: 32-bit checkpoints, r images, 1/s
             l.slots = std::min(l.count, kWarpSlotCap);
             long long words = v->slot_words(T_max);
-            if (v->warp == 3) {                          // second tier: the fp64 warp variant of the same NS shares the slots
+            if (v->warp >= 3) {                          // second tier: the fp64 warp variant of the same NS shares the slots
                 int n2 = 0;
                 const Variant *t2 = ladder_table(LADDER_WARP, vch, &n2);
                 for (int i = 0; i < n2; ++i)
@@ -237,22 +237,42 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
         const int n = (int)plan.launches.size();
         const bool ranges = n > 1 && n <= sms && !std::getenv("CTC_B200_FULL_GRIDS");
-        double tot = 0.0, acc = 0.0;
-        for (const Plan::Launch &l : plan.launches) tot += (double)std::max<long long>(l.frames, 1) * warp_rel_cost(l.v);
+        std::vector<int> per_sm(n), nsm(n, 1);
+        for (int i = 0; i < n; ++i)
+            per_sm[i] = std::max(1, persistent_grid((const void *)plan.launches[i].v->kernel, plan.launches[i].smem) / sms);
+        if (ranges) {
+            // Estimated finish time of bucket i on m SMs: work / m (a fluid model; counting whole rounds of utterances per
+            // resident warp instead was measured to be worse -- warps speed up as their neighbours retire).  Start from
+            // one SM each and hand the remaining SMs, one at a time, to the bucket that currently finishes last.
+            auto finish = [&](int i, int m) {
+                const Plan::Launch &l = plan.launches[i];
+                return (double)std::max<long long>(l.frames, 1) * warp_rel_cost(l.v) / m;
+            };
+            for (int left = sms - n; left > 0; --left) {
+                int worst = 0;
+                double tw = -1.0;
+                for (int i = 0; i < n; ++i) {
+                    const double t = finish(i, nsm[i]);
+                    if (t > tw) { tw = t; worst = i; }
+                }
+                ++nsm[worst];
+            }
+            int used = 0;
+            for (int i = 0; i < n; ++i) used += nsm[i];
+            for (int i = 0; used < sms; i = (i + 1) % n, ++used) ++nsm[i];   // leftovers: spread
+        }
         int cut = 0;
         for (int i = 0; i < n; ++i) {
             Plan::Launch &l = plan.launches[i];
-            const int per_sm = std::max(1, persistent_grid((const void *)l.v->kernel, l.smem) / sms);
             if (ranges) {
-                acc += (double)std::max<long long>(l.frames, 1) * warp_rel_cost(l.v);
-                int next = (i == n - 1) ? sms : (int)std::lround(sms * acc / tot);
-                next = std::max(next, cut + 1);                     // at least one SM each ...
-                next = std::min(next, sms - (n - 1 - i));           // ... and room for the buckets still to come
-                l.sm_lo = cut; l.sm_hi = next;
-                cut = next;
-                l.slots = std::min(l.count, per_sm * (l.sm_hi - l.sm_lo) + 1);
+                l.sm_lo = cut; l.sm_hi = cut + nsm[i];
+                cut = l.sm_hi;
+                l.slots = std::min(l.count, per_sm[i] * nsm[i] + 1);
+                if (!size_only && std::getenv("CTC_B200_PLAN_DEBUG"))
+                    std::fprintf(stderr, "bucket NS=%d count=%d per_sm=%d SMs [%d,%d) rounds %.2f\n", l.v->NS, l.count, per_sm[i],
+                                 l.sm_lo, l.sm_hi, (double)l.count / (per_sm[i] * nsm[i]));
             } else {
-                l.slots = std::min(l.count, per_sm * sms);
+                l.slots = std::min(l.count, per_sm[i] * sms);
             }
         }
     }
@@ -380,7 +400,7 @@ double warp_rel_cost(const Variant *v)
     static const double c64[9] = {0, 1.20, 1.44, 1.80, 2.21, 2.70, 3.28, 3.80, 4.33};   // NS = 2 .. 16, fp64 recursion
     static const double c32[9] = {0, 1.05, 1.27, 1.55, 1.77, 2.01, 2.43, 2.70, 3.03};   // fp32 recursion
     const int i = std::max(1, std::min(v->NS / 2, 8));
-    return v->warp == 3 ? c32[i] : c64[i];
+    return v->warp >= 3 ? c32[i] : c64[i];
 }
 
 // Enqueue the device-side log-space detour behind the fast kernels of this call (ctc_logspace.cuh): persistent CTAs

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(kLogThreads) ctc_logspace_kernel(const LogPara
         if (!(st & (UTT_RANGE | UTT_INF_COST)) || (st & UTT_BAD_LABEL)) continue;
         const int ustat = logspace_utterance(P, b, smem);
         __syncthreads();
-        if (threadIdx.x == 0) P.status[b] = ustat | UTT_LOGSPACE;
+        if (threadIdx.x == 0) P.status[b] = ustat | UTT_LOGSPACE | (st & UTT_WIDE);
     }
 }
 

@@ -19,12 +19,12 @@ struct Variant {
     int max_label() const { return (32 * NS * W) / 2 - 1; }   // SP = 32*NS*W states must hold 2L+2
     int smem_bytes(int V, int T_max) const
     {
-        return warp == 3 ? make_warp32_layout(NS, K, VCH).total
+        return warp >= 3 ? make_warp32_layout(NS, K, VCH).total
                : warp ? make_warp_layout(NS, K, VCH, warp == 2).total : make_layout(NS, W, K, V, T_max).total;
     }
     long long slot_words(int T_max) const      // warp ladders: 4-byte words of workspace per resident CTA
     {
-        return warp == 3 ? warp32_slot_words(NS, K, VCH, T_max) : warp_slot_words(NS, K, VCH, T_max);
+        return warp >= 3 ? warp32_slot_words(NS, K, VCH, T_max) : warp_slot_words(NS, K, VCH, T_max);
     }
     int sp() const { return 32 * NS * W; }
 };

@@ -29,10 +29,16 @@
 //  * checkpoint = the fp32 column + the 32 exponents (one more 128-byte row per chunk).
 //  * backward: the checkpoint column of lane l is scaled by 2^(ea_l + eb_l - ez) (Z^ = mz * 2^ez), so the products
 //    alpha * tb are posteriors in units of mz; the scaled column lives in the frame 2^(ez - eb_l), i.e. its neighbour
-//    factor is 2^(eb_l - eb_{l-1}).  Entries are clamped to 2^110 (a clamped entry meets a tb below 2^-109).
-//  * the mass check of a chunk, q = sum_s alpha(t0, s) * tb(t0, s) / Z^ (= 1 in exact arithmetic), is (a) the range
-//    self-check as in ctc_warp.cuh and (b) DIVIDED OUT of the chunk's posteriors: the rounding drift of two T-step
-//    fp32 product chains (up to ~2e-5 at T = 1500) cancels, what is left is the rounding inside one chunk.
+//    factor is 2^(eb_l - eb_{l-1}).
+//  * mass checks: q(t) = sum_s alpha(t, s) * tb(t, s) = Z^ at every frame.  It is formed at the FIRST and the LAST
+//    frame of every chunk.  The first frame's value is (a) DIVIDED OUT of the chunk's posteriors, which removes the
+//    rounding drift of the two T-step fp32 product chains (up to ~2e-5 at T = 1500), and (b) compared with the
+//    previous chunk's: the beta recursion is linear with positive terms, so mass it loses to underflow anywhere in the
+//    chunk never arrives at the first frame.  The last frame's value is compared with the first: mass the recomputed
+//    alpha recursion loses (underflow in a lane frame that is fixed for the chunk while a narrow band of live states
+//    sweeps through it, overflow of the scaled column) never arrives there.  Either deficit above 4e-6 flags the
+//    utterance.  A check at the first frame alone is NOT enough in fp32 (found by the parity fuzz: sigma = 4 logits with
+//    T = L + 12 gave a wrong gradient at frames in mid-chunk with a clean first-frame check).
 //  * the blank gradient of a frame is minus the sum of the other gradients of the row (sum_k p = sum_k posterior = 1).
 //
 // Everything else (prologue, product slots grouped by symbol, conflict-free gather, cp.async staging of the backward
@@ -48,7 +54,7 @@ constexpr int kW32TargetA = 100;        // forward: group max at 2^100 (growth 3
 constexpr int kW32TargetB = 40;         // backward: alpha_scaled * tb ~ posterior, the two ranges are reciprocal
 constexpr int kW32Lip = 64;
 constexpr int kW32Dead = -(1 << 28);
-constexpr float kW32Clamp = 1.298074214633707e33f;   // 2^110
+
 
 struct Warp32Layout {
     int PS;
@@ -140,7 +146,9 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
     // lanes mass can arrive from within one chunk: ceil(2K / NS); the window is the next power of two above it
     constexpr int REACH = (2 * K + NS - 1) / NS;
     constexpr int WIN = REACH >= 16 ? 32 : REACH >= 8 ? 16 : REACH >= 4 ? 8 : REACH >= 2 ? 4 : 2;
-    constexpr float kCheckTol = 1e-4f;
+    constexpr float kCheckTol = 1e-4f;            // drift of the two T-step product chains against Z^ (divided out)
+    constexpr float kJumpTol = 4e-6f;             // mass of a chunk's first frame against the previous chunk's, of its last frame
+                                                  // against its first
     constexpr float L2E = 1.4426950408889634f;
 
     extern __shared__ __align__(16) unsigned char smem[];
@@ -346,10 +354,9 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             return v;
         };
         // one alpha step in place (descending i keeps the old neighbours intact).  fu brings the lower lane's top state
-        // into this lane's frame; capped: the scaled column of the backward sweep (clamped to 2^110).
-        auto alpha_step = [&](auto capped, float (&a)[NS], const float (&row)[VCH], float pb, float fu) {
-            float up1 = __shfl_up_sync(kFull, a[NS - 1], 1) * fu;
-            if (decltype(capped)::value) up1 = fminf(up1, kW32Clamp);
+        // into this lane's frame.
+        auto alpha_step = [&](float (&a)[NS], const float (&row)[VCH], float pb, float fu) {
+            const float up1 = __shfl_up_sync(kFull, a[NS - 1], 1) * fu;
 #pragma unroll
             for (int i = NS - 1; i >= 0; --i) {
                 if (i & 1) {
@@ -429,7 +436,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
                 if (lane < KK) invw[t0 + lane] = myinv;
             }
 #pragma unroll
-            for (int tt = 0; tt < KK; ++tt) alpha_step(std::false_type(), a, rcur[tt], pbv[tt], fu);
+            for (int tt = 0; tt < KK; ++tt) alpha_step(a, rcur[tt], pbv[tt], fu);
         };
 
         if (nfull > 0) load_rows(std::integral_constant<int, K>(), 0);
@@ -479,7 +486,8 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
         for (int i = 0; i < NS; ++i) bt[i] = (lane * NS + i == S - 1) ? exp2i(kW32TargetB) : 0.f;   // virtual column t = T
         int eb = -kW32TargetB;
         float fd = (lane == 31) ? 0.f : 1.f;
-        float chk_dev = 0.f;
+        float chk_dev = 0.f, jmp_dev = 0.f;
+        float rq_prev = inv_mz;                             // 1 / (mass at the first frame of the previous chunk); Z^ to start with
         unsigned pmax = 0u;                                 // largest per-symbol product sum seen (must stay below ~2)
 
         float *stg = (float *)(smem + lay.off_stg);         // [NS + 1][32] column, exponents | [K][VCH][32] rows | [K] 1/s
@@ -525,9 +533,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             if (next == 2) stage(std::integral_constant<int, K>(), t0n, cin);
             else if (next == 1) stage(std::integral_constant<int, 1>(), t0n, cin);
             // posterior scale of this lane: alpha_sc = alpha^ * 2^(eb - ez)
-            scale32<NS>(a, ea_c + eb - ez);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) a[i] = fminf(a[i], kW32Clamp);
+            scale32<NS>(a, ea_c + eb - ez);               // (no clamp: an overflow ends as inf / NaN in the mass check below)
             float fa;
             {
                 const int ebl = __shfl_up_sync(kFull, eb, 1);
@@ -541,20 +547,20 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
 
             // -- recompute alpha inside the chunk from its checkpoint; keep the label states --
             float av[KK][NL];
-            float ab[NL];                                   // blank states of the first frame (mass check)
+            float ab0[NL], ab1[NL];                         // blank states of the chunk's first and last frame (mass checks)
 #pragma unroll
             for (int tt = 0; tt < KK; ++tt) {
-                alpha_step(std::true_type(), a, rcur[tt], pbv[tt], fa);
+                alpha_step(a, rcur[tt], pbv[tt], fa);
 #pragma unroll
-                for (int jj = 0; jj < NL; ++jj) av[tt][jj] = a[2 * jj + 1];
-                if (tt == 0) {
-#pragma unroll
-                    for (int jj = 0; jj < NL; ++jj) ab[jj] = a[2 * jj];
+                for (int jj = 0; jj < NL; ++jj) {
+                    av[tt][jj] = a[2 * jj + 1];
+                    if (tt == 0) ab0[jj] = a[2 * jj];
+                    if (tt == KK - 1) ab1[jj] = a[2 * jj];
                 }
             }
 
             // -- beta over the chunk; products alpha * tb go to shared memory grouped by symbol --
-            float q = 0.f;
+            float qf = 0.f, ql = 0.f;                       // this lane's share of sum_s alpha(t, s) * tb(t, s) at t0 and at t1 - 1
 #pragma unroll
             for (int tt = KK - 1; tt >= 0; --tt) {
                 const float dn0 = __shfl_down_sync(kFull, bt[0], 1) * fd, dn1 = __shfl_down_sync(kFull, bt[1], 1) * fd;
@@ -568,25 +574,44 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
                         const float n2 = (i + 2 < NS) ? bt[i + 2] : dn1;   // (msk[NL] is 0 on lane 31)
                         const float tb = fmaf(msk[jj + 1], n2, s1);
                         const float pr = av[tt][jj] * tb;
-                        if (tt == 0) q += pr;
+                        if (tt == 0) qf += pr;
+                        if (tt == KK - 1 && KK > 1) ql += pr;
                         prow[sl[jj]] = pr;
                         bt[i] = tb * pl;
                     } else {
                         const float tb = bt[i] + bt[i + 1];
-                        if (tt == 0) q = fmaf(ab[i >> 1], tb, q);
+                        if (tt == 0) qf = fmaf(ab0[i >> 1], tb, qf);
+                        if (tt == KK - 1 && KK > 1) ql = fmaf(ab1[i >> 1], tb, ql);
                         bt[i] = tb * pbv[tt];
                     }
                 }
             }
             __syncwarp();                                   // products visible to the gather
 
-            // -- mass check of frame t0, divided out of the chunk's posteriors --
+            // -- mass checks.  sum_s alpha(t, s) * tb(t, s) = Z^ at every frame; all terms are positive and both
+            //    recursions are linear, so relevant mass lost (flushed, denormal, overflowed) on the way shows as a deficit
+            //    where the recursion that lost it ends: the beta recursion at the chunk's FIRST frame (a jump against the
+            //    previous chunk's value; mass lost by the forward sweep makes Z^ itself too small and shows the same way),
+            //    the recomputed alpha recursion at its LAST frame.  The frames in between need no check of their own:
+            //    their products are made of the same alpha and tb values.  The first frame's sum also replaces Z^ for the
+            //    chunk's posteriors, which removes the rounding drift of the two T-step fp32 product chains. --
             float scale = 0.f;
-            if (z_ok) {
-                const float qs = warp_sum_f(q) * inv_mz;
-                const float dev = qs - 1.f;
-                chk_dev = fmaxf(chk_dev, (dev == dev) ? fabsf(dev) : INFINITY);
-                scale = __fdividef(inv_mz, qs);
+            {
+                float two[2] = {qf, ql};
+                const float mine = warp_sum_transposed<2>(two, lane);       // even lanes: first frame, odd lanes: last
+                const float q0 = __shfl_sync(kFull, mine, 0);
+                const float q1 = (KK > 1) ? __shfl_sync(kFull, mine, 1) : q0;
+                if (z_ok) {
+                    const float dev = q0 * inv_mz - 1.f;
+                    chk_dev = fmaxf(chk_dev, (dev == dev) ? fabsf(dev) : INFINITY);
+                    const float dj = q0 * rq_prev - 1.f;
+                    const float rq0 = __frcp_rn(q0);
+                    const float dl = q1 * rq0 - 1.f;
+                    const float d2 = fmaxf((dj == dj) ? fabsf(dj) : INFINITY, (dl == dl) ? fabsf(dl) : INFINITY);
+                    jmp_dev = fmaxf(jmp_dev, d2);
+                    rq_prev = rq0;
+                    scale = rq0;                                            // posterior = products / (their own sum at t0)
+                }
             }
 
             // -- gather: lane k sums the products of symbol k for the KK frames of the chunk --
@@ -641,7 +666,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
         for (int c = nfull - 1; c >= 0; --c)
             bwd_chunk(std::integral_constant<int, K>(), c * K, (c >= 1) ? 2 : 0, (c - 1) * K, c - 1);
 
-        if (!(chk_dev <= kCheckTol) || pmax > 0x40100000u) ustat |= UTT_RANGE;   // (acc = posterior * mz * q < 2; NaN / inf land here)
+        if (!(chk_dev <= kCheckTol) || !(jmp_dev <= kJumpTol) || pmax > 0x40100000u) ustat |= UTT_RANGE;   // (acc = posterior * mz * q < 2; NaN / inf land here)
         if (__any_sync(kFull, ustat & UTT_RANGE)) ustat |= UTT_RANGE;
         if (lane == 0) P.status[b] = ustat;
         if (P.debug && lane == 0) {                         // development aid: what the self-checks saw
@@ -649,6 +674,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             P.debug[b * 16 + 1] = pmax;
             P.debug[b * 16 + 2] = hmax;
             P.debug[b * 16 + 3] = ustat;
+            P.debug[b * 16 + 4] = __float_as_uint(jmp_dev);
         }
         // padded frames get zero gradient
         for (int t = T; t < P.T_max; ++t)

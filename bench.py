@@ -430,6 +430,7 @@ def main():
             "workload": f"B={B}, blank +6 on 70 % of frames / aligned label +6 otherwise, act_lens in [0.6 T, T], L <= T/4",
             "ms_per_call": pk_ms, "utterances_per_s": B / (pk_ms * 1e-3),
             "logspace_detour_rate": float((st_p & 16).ne(0).float().mean().item()),
+            "fp64_tier_rate": float((st_p & 32).ne(0).float().mean().item()),
             "infeasible": int((st_p & 1).ne(0).sum().item()), "range_flag_left": int((st_p & 8).ne(0).sum().item())}
         del ap_h, ap_d
 

@@ -181,6 +181,8 @@ def ctc_single(acts_tv, labels, blank=0, K=8, NS=None, seed=0, return_check=Fals
         zloc += float(flat(a)[S - 2]) * 2.0 ** float(np.clip(int(ea[lane_of[S - 2]]) - e_ref, -1000, 1000))
     if not (zloc > 0) or not np.isfinite(zloc):
         grad[:] = p32
+        if return_check == "flags":
+            return np.inf, grad, np.inf, dict(drift=True, jump=True, last=True)
         return (np.inf, grad, np.inf) if return_check else (np.inf, grad)
     cost = -(np.log(zloc) + e_ref * np.log(2.0) - logs.sum())
     mz, ezl = np.frexp(zloc)
@@ -191,28 +193,46 @@ def ctc_single(acts_tv, labels, blank=0, K=8, NS=None, seed=0, return_check=Fals
     flat(b)[S - 1] = F(2.0 ** TB)
     eb = np.full(NLANES, -TB, dtype=np.int64)
     worst = 0.0
+    flags = dict(drift=False, jump=False, last=False)
+    q_prev = None
     for c in range(nC - 1, -1, -1):
         t0, t1 = c * K, min(T, (c + 1) * K)
         esc = ck_e[c] + eb - ez
         # the scaled column a_sc = alpha^ * 2^(eb_l - ez) lives in the per-lane frame e'_l = ez - eb_l, so the neighbour
-        # factor of the recompute is 2^(eb_l - eb_{l-1}) (<= 2^64 by the Lipschitz rule); entries are clamped to 2^110
-        a = np.minimum(_scale(ck[c], esc), F(2.0 ** 110))
-        eframe = ez - eb
-        acol = []
-        for t in range(t0, t1):
-            a = np.minimum(a_step(a, eframe, emit[t]), F(2.0 ** 110))
-            acol.append(a)
-        # beta over the chunk; the products wait (shared memory in the kernel) until the chunk's first frame has been
-        # reached: q = sum_s alpha_sc(t0, s) * tb(t0, s) / mz is 1 in exact arithmetic.  Its deviation is (a) the range
-        # self-check and (b) with renorm, the rounding drift of the two T-step product chains, which is divided out of
-        # the chunk's posteriors (the "posterior normalised per chunk" of SURVEY.md Appendix D, schemes B / D)
-        prods = []
-        for t in range(t1 - 1, t0 - 1, -1):
-            tb = b_pre(b, eb)
-            b = (flat(tb) * emit[t]).astype(F).reshape(NLANES, NS)
-            prods.append((t, (flat(acol[t - t0]) * flat(tb)).astype(F)))
+        # factor of the recompute is 2^(eb_l - eb_{l-1}) (<= 2^64 by the Lipschitz rule).  No clamp: an overflow ends as
+        # inf / NaN in the mass check of the chunk's last frame.
+        with np.errstate(over="ignore", invalid="ignore"):
+            a = _scale(ck[c], esc)
+            eframe = ez - eb
+            acol = []
+            for t in range(t0, t1):
+                a = a_step(a, eframe, emit[t])
+                acol.append(a)
+            prods = []
+            for t in range(t1 - 1, t0 - 1, -1):
+                tb = b_pre(b, eb)
+                b = (flat(tb) * emit[t]).astype(F).reshape(NLANES, NS)
+                prods.append((t, (flat(acol[t - t0]) * flat(tb)).astype(F)))
+        # -- mass checks: sum_s alpha_sc(t, s) * tb(t, s) = Z^ at the chunk's FIRST frame (against Z^: the drift of the two
+        #    product chains, divided out of the chunk's posteriors) and at its LAST frame (against the first).  All terms
+        #    are positive and both recursions are linear, so
+        #      * relevant mass lost (flushed, denormal) by the beta recursion at any frame of the chunk never arrives at
+        #        the first frame: a deficit there, i.e. a jump against the previous chunk's value;
+        #      * relevant mass lost (flushed, overflowed) by the recomputed alpha recursion at any frame of the chunk
+        #        never arrives at the last frame: a deficit there;
+        #      * mass lost by the forward sweep makes Z^ itself too small: a jump between the chunks around the loss.
+        #    The frames in between need no check of their own (and no storage of their blank states). --
         q = float(prods[-1][1][valid].astype(np.float64).sum()) / mz
+        q_last = float(prods[0][1][valid].astype(np.float64).sum()) / mz
         worst = max(worst, abs(q - 1.0) if np.isfinite(q) else np.inf)
+        if not np.isfinite(q) or abs(q - 1.0) > 1e-4:
+            flags["drift"] = True
+        ref = q_prev if q_prev is not None else 1.0
+        if not np.isfinite(q) or abs(q / ref - 1.0) > 4e-6:
+            flags["jump"] = True
+        if not np.isfinite(q_last) or abs(q_last / q - 1.0) > 4e-6:
+            flags["last"] = True
+        q_prev = q
         scale = F(inv_mz / F(q)) if (renorm and np.isfinite(q) and q > 0) else inv_mz
         for t, prod in prods:
             acc = np.zeros(V, dtype=F)
@@ -226,6 +246,8 @@ def ctc_single(acts_tv, labels, blank=0, K=8, NS=None, seed=0, return_check=Fals
         en = _lane_exps(b, eb, TB, reach, upward=False)
         b = _scale(b, eb - en)
         eb = en
+    if return_check == "flags":
+        return float(cost), grad, worst, flags
     if return_check:
         return float(cost), grad, worst
     return float(cost), grad

@@ -42,7 +42,7 @@ def _assert_close(costs, grads, ref_costs, ref_grads, tag=""):
                                       f"per-utt max {d.max(axis=(0, 2))}")
 
 
-@pytest.mark.parametrize("mode", ["warp", "throughput", "throughput8", "latency", "latency3"])
+@pytest.mark.parametrize("mode", ["warp32", "warp", "throughput", "throughput8", "latency", "latency3"])
 @pytest.mark.parametrize("case", KNOWN, ids=[c["name"] for c in KNOWN])
 def test_known_answers(case, mode):
     from oracle import ctc_f64
@@ -60,7 +60,7 @@ def test_known_answers(case, mode):
     _assert_close(costs, grads, oc, og, case["name"])
 
 
-@pytest.mark.parametrize("mode", ["warp", "throughput", "throughput8", "latency", "latency3"])
+@pytest.mark.parametrize("mode", ["warp32", "warp", "throughput", "throughput8", "latency", "latency3"])
 @pytest.mark.parametrize("name", sorted(TORCH_CASES))
 def test_golden_torch_f64(name, mode):
     c = TORCH_CASES[name]
@@ -85,7 +85,7 @@ SYNTH = {
 }
 
 
-@pytest.mark.parametrize("mode", ["warp", "throughput", "throughput8", "latency", "latency3"])
+@pytest.mark.parametrize("mode", ["warp32", "warp", "throughput", "throughput8", "latency", "latency3"])
 @pytest.mark.parametrize("name", sorted(SYNTH))
 def test_synthetic_vs_f64_oracle(name, mode):
     from oracle import ctc_f64
@@ -106,7 +106,7 @@ def test_edge_cases_batch():
     al = np.array([24, 10, 11, 12, 8, 1, 1, 20], np.int32)
     labels = np.concatenate([np.full(18, 3), rng.integers(1, V, 9), [4], rng.integers(1, V, 5)]).astype(np.int32)
     acts = rng.standard_normal((T, len(ll), V)).astype(np.float32)
-    for mode in ("warp", "throughput", "throughput8", "latency", "latency3"):
+    for mode in ("warp32", "warp", "throughput", "throughput8", "latency", "latency3"):
         costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
         oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
         _assert_close(costs, grads, oc, og, "edge/" + mode)
@@ -337,7 +337,7 @@ def test_bitwise_reproducible_and_stream_safe():
     a = torch.tensor(acts).cuda()
     args = [torch.tensor(x) for x in (labels, al, ll)]
     side = torch.cuda.Stream()
-    for mode, bidir in (("warp", False), ("throughput", False), ("throughput8", False), ("latency", True), ("latency", False), ("auto", True)):
+    for mode, bidir in (("warp32", False), ("warp", False), ("throughput", False), ("throughput8", False), ("latency", True), ("latency", False), ("auto", True)):
         c0, g0, s0 = ctc_loss_raw(a, *args, mode=mode, bidirectional=bidir)
         for _ in range(3):
             c1, g1, s1 = ctc_loss_raw(a, *args, mode=mode, bidirectional=bidir)
@@ -383,7 +383,7 @@ def test_two_threads_two_streams():
 
 # ---- round-2 additions: parity soft spots named by the round-1 review -------------------------------------------
 
-@pytest.mark.parametrize("mode", ["warp", "latency", "throughput8"])
+@pytest.mark.parametrize("mode", ["warp32", "warp", "latency", "throughput8"])
 def test_against_fp32_warpctc_cpu_port_small_t(mode):
     """north_star: "match the reference's warp-ctc ... cross-checked against float64".  warp-ctc's CPU arithmetic
     (fp32 log space, oracle/warpctc_cpu.c) subtracts numbers of size |log Z| ~ 2.8 T, so its own distance to float64
@@ -418,7 +418,7 @@ def test_config3_full_size():
     labels = rng.integers(1, V, int(ll.sum())).astype(np.int32)
     acts = rng.standard_normal((T_max, B, V)).astype(np.float32)
     oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
-    for mode in ("auto", "warp"):
+    for mode in ("auto", "warp32", "warp"):
         costs, grads, status = _engine(acts, labels, al, ll, 0, mode)
         _assert_close(costs, grads, oc, og, "c3/" + mode)
         assert not status.any()
@@ -450,7 +450,7 @@ def test_config4_full_batch():
     oracle = {}
     for b in picks:
         oracle[b] = ctc_f64.ctc_batch(acts[:, b:b + 1].numpy(), labels[offs[b]:offs[b] + ll[b]].numpy(), [T], [int(ll[b])])
-    for mode in ("auto", "warp"):
+    for mode in ("auto", "warp32", "warp"):
         costs, grads, status = ctc_loss_raw(d_acts, labels, al, ll, mode=mode)
         assert not status.any(), mode
         assert torch.isfinite(costs).all() and torch.isfinite(grads).all()
@@ -489,7 +489,7 @@ def test_bounded_fuzz_slice():
         oc, og = ctc_f64.ctc_batch(acts, labels, al, ll, blank)
         a = torch.tensor(acts).cuda()
         args = [torch.tensor(x) for x in (labels, al, ll)]
-        for mode, bidir in (("warp", False), ("auto", True), ("throughput8", False), ("latency", False)):
+        for mode, bidir in (("warp32", False), ("warp", False), ("auto", True), ("throughput8", False), ("latency", False)):
             c, g, st = ctc_loss_raw(a, *args, blank=blank, mode=mode, bidirectional=bidir)
             c = c.numpy().astype(np.float64)
             g = g.cpu().numpy().astype(np.float64)
@@ -499,3 +499,30 @@ def test_bounded_fuzz_slice():
             eg = float(np.abs(g - og).max())
             worst = max(worst, eg)
             assert el <= LOSS_RTOL and eg <= GRAD_ATOL, (case, mode, V, T, B, lmax, blank, sigma, el, eg, sorted(set(st.tolist())))
+
+
+def test_fp32_ladder_hands_wide_range_utterances_to_the_fp64_tier():
+    """ctc_warp32_kernel (fp32 recursion, per-lane block exponents) holds ~2^226 of range inside a lane group, the fp64
+    kernels 2^1266 inside a column.  Wide logit distributions (sigma >= 4) and confident-and-wrong models leave the
+    fp32 range; its mass self-check must flag them, the fp64 warp kernel of the same label class redoes them
+    (status bit 0x20), and whatever that kernel flags in turn goes to the log-space kernel (0x10).  The result is within
+    the north_star tolerances whichever tier produced it, and benign inputs never leave the first tier."""
+    from oracle import ctc_f64
+    seen_wide = 0
+    for seed, kw in enumerate((dict(T=400, B=6, V=43, lmin=30, lmax=120, sigma=4.0), dict(T=300, B=16, V=29, lmin=20, lmax=100, sigma=6.0),
+                               dict(T=750, B=8, V=29, lmin=50, lmax=200, sigma=3.0))):
+        acts, labels, al, ll = synth_problem(seed=15 + seed, **kw)
+        oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
+        costs, grads, status = _engine(acts, labels, al, ll, 0, "warp32")
+        _assert_close(costs, grads, oc, og, f"fp32-tiers/{seed}")
+        assert not (status & 0x8).any(), status
+        seen_wide += int(((status & 0x20) != 0).sum())
+    assert seen_wide > 0, "expected the sigma >= 4 cases to use the fp64 tier"
+    acts, labels, al, ll = synth_problem(41, 750, 32, 29, 50, 200)
+    costs, grads, status = _engine(acts, labels, al, ll, 0, "warp32")
+    assert not np.asarray(status).any(), "benign N(0,1) logits must stay in the fp32 tier"
+    # forcing the first tier only (no fallback) must report, not hide, what it could not do
+    from aes_lac_2018_b200 import ctc_loss_raw
+    acts, labels, al, ll = synth_problem(16, 300, 16, 29, 20, 100, sigma=6.0)
+    _, _, st = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), mode="warp32", no_fallback=True)
+    assert (st & 0x8).any()

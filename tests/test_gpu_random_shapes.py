@@ -38,7 +38,7 @@ def test_random_shapes_all_ladders(seed):
     oc, og = ctc_f64.ctc_batch(acts, labels, al, ll, blank)
     a = torch.tensor(acts).cuda()
     args = [torch.tensor(x) for x in (labels, al, ll)]
-    for mode, bidir in (("warp", True), ("throughput", True), ("throughput8", True), ("latency", True), ("latency", False)):
+    for mode, bidir in (("warp32", True), ("warp", True), ("throughput", True), ("throughput8", True), ("latency", True), ("latency", False)):
         costs, grads, status = ctc_loss_raw(a, *args, blank=blank, mode=mode, bidirectional=bidir)
         c = costs.numpy().astype(np.float64)
         g = grads.cpu().numpy().astype(np.float64)
@@ -71,7 +71,7 @@ def test_variant_capacity_edges(L):
     oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
     a = torch.tensor(acts).cuda()
     args = [torch.tensor(x) for x in (labels, al, ll)]
-    for mode, bidir in (("warp", False), ("throughput", False), ("throughput8", False), ("latency", True), ("latency", False)):
+    for mode, bidir in (("warp32", False), ("warp", False), ("throughput", False), ("throughput8", False), ("latency", True), ("latency", False)):
         costs, grads, status = ctc_loss_raw(a, *args, mode=mode, bidirectional=bidir)
         tag = f"L {L} T {T} V {V} mode {mode} bidir {bidir}"
         assert status.numpy()[0] == 0, tag + f" status {status.numpy()[0]}"      # in particular: no log-space detour

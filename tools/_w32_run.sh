@@ -1,6 +1,4 @@
-timeout 300 python tools/warp_dev.py --modes=warp32,warp --pmodes=warp32,warp 2>&1 | tee gpurun_out/w32_dev3.log | grep -v " ok$" | tail -20
-for env in "X=1" "CTC_B200_FULL_GRIDS=1"; do
-echo "== $env"
-env $env ALT_MODE=warp32 python tools/warp_alt_time.py "50-200,100-140" default mix1 2>&1 | tee -a gpurun_out/w32_alt4.log
-env $env ALT_MODE=warp python tools/warp_alt_time.py "50-200" default 2>&1 | tee -a gpurun_out/w32_alt4.log
-done
+python tools/w32_case.py 5079 warp32 2>&1 | grep "b=13"
+timeout 300 python tools/warp_dev.py --pmodes=warp32 --modes=warp32 2>&1 | grep -v " ok$" | tee gpurun_out/w32_dev4.log | head -14
+timeout 900 python tools/fuzz.py 400 7000 2>&1 | tail -6 | tee gpurun_out/fuzz_w32c.log
+python -m pytest tests -m gpu -q --no-header -rf -p no:cacheprovider --timeout 900 -x 2>&1 | tail -6 | tee gpurun_out/pytest_gpu_w32b.log

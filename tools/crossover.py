@@ -14,7 +14,7 @@ for B in (32, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536, 2048, 4096):
     al = torch.full((B,), T, dtype=torch.int32)
     labels = torch.randint(1, V, (int(ll.sum()),), generator=g, dtype=torch.int32)
     row = []
-    for mode in ("warp", "latency", "auto"):
+    for mode in ("warp32", "warp", "latency", "auto"):
         for _ in range(3):
             ctc_loss_raw(acts, labels, al, ll, mode=mode)
         best = 1e9

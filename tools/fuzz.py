@@ -32,7 +32,7 @@ for case in range(n_cases):
     oc, og = ctc_f64.ctc_batch(acts, labels, al, ll, blank)
     a = torch.tensor(acts).cuda()
     args = [torch.tensor(x) for x in (labels, al, ll)]
-    for mode, bidir in (("auto", True), ("throughput", False), ("throughput8", False), ("latency", True), ("latency", False)):
+    for mode, bidir in (("auto", True), ("warp32", False), ("warp", False), ("throughput", False), ("throughput8", False), ("latency", True), ("latency", False)):
         c, g, st = ctc_loss_raw(a, *args, blank=blank, mode=mode, bidirectional=bidir)
         c = c.numpy().astype(np.float64); g = g.cpu().numpy().astype(np.float64)
         fin = np.isfinite(oc)
@@ -46,4 +46,4 @@ for case in range(n_cases):
             bad += 1
             print(f"FAIL case {seed0 + case} mode {mode} bidir {bidir}: V {V} T {T} B {B} L {ll.tolist()} T_b {al.tolist()} blank {blank} sigma {sigma} "
                   f"loss err {el:.2e} grad err {eg:.2e} status {sorted(set(st.tolist()))}", flush=True)
-print(f"{n_cases} cases x 5 paths in {time.time() - t0:.0f}s: failures {bad}, worst loss rel err {worst['loss']:.2e}, worst grad abs err {worst['grad']:.2e}")
+print(f"{n_cases} cases x 7 paths in {time.time() - t0:.0f}s: failures {bad}, worst loss rel err {worst['loss']:.2e}, worst grad abs err {worst['grad']:.2e}")
