@@ -44,7 +44,7 @@ constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBidirMaxB = 160;             // bidirectional (two sweeps + combine) path for batches up to this size ...
 constexpr size_t kBidirMaxBytes = 1u << 30;     // ... and up to this many bytes of spilled columns (B = 128, T = 1500,
                                                 // L <= 200 -- one eighth of BASELINE configs[3] -- needs 786 MB)
-constexpr int kWarpMinB = 1024;             // automatic ladder choice: warp ladder from this batch size (measured crossover,
+constexpr int kWarpMinB = 512;              // automatic ladder choice: warp ladder from this batch size (measured crossover,
                                             // profiles/r2_crossover.txt)
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
 constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)
@@ -398,7 +398,7 @@ int persistent_grid(const void *kernel, int smem)
 double warp_rel_cost(const Variant *v)
 {
     static const double c64[9] = {0, 1.20, 1.44, 1.80, 2.21, 2.70, 3.28, 3.80, 4.33};   // NS = 2 .. 16, fp64 recursion
-    static const double c32[9] = {0, 1.05, 1.27, 1.55, 1.77, 2.01, 2.43, 2.70, 3.03};   // fp32 recursion
+    static const double c32[9] = {0, 1.07, 1.28, 1.54, 1.79, 2.07, 2.46, 2.70, 3.18};   // fp32 recursion
     const int i = std::max(1, std::min(v->NS / 2, 8));
     return v->warp >= 3 ? c32[i] : c64[i];
 }

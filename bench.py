@@ -307,7 +307,7 @@ def main():
     loss_total = float(last["total"].item())
     local_sum = float(last["local"].item())
     status_or = 0
-    for bit in (1, 2, 4, 8, 16):
+    for bit in (1, 2, 4, 8, 16, 32):
         if bool((last["status"] & bit).any().item()):
             status_or |= bit
     gathered = [local_sum]
@@ -489,7 +489,7 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": "ctc_warp_kernel<NS,8,1,*> (the variant launches of one call, overlapped on forked streams)",
+                         "kernel": "ctc_warp32_kernel<NS,8,1,*> (fp32 recursion with per-lane block exponents; the per-label-class launches of one call run side by side on disjoint SM ranges)",
                          "algorithmic_bytes_per_call": alg_bytes, "kernel_ms_per_call": kernel_ms},
             "blocking_dropin": {"ms_per_step": blocking_ms, "utterances_per_s": B * world / (blocking_ms * 1e-3),
                                 "what": "same engine call with upstream's blocking contract (costs and status read back every step)"},

@@ -14,17 +14,25 @@ small = synth_problem(1, 50, 5, 29, 0, 20, tmin=30)
 mid = synth_problem(2, 70, 3, 43, 40, 150 // 2, tmin=60)
 wide = synth_problem(3, 300, 1, 29, 140, 140)
 for name, prob in (("small", small), ("mid", mid), ("wide", wide)):
-    for mode, bidir in (("warp", False), ("throughput", True), ("throughput8", True), ("latency", True), ("latency", False)):
+    for mode, bidir in (("warp32", False), ("warp", False), ("throughput", True), ("throughput8", True), ("latency", True), ("latency", False)):
         run(f"{name}/{mode}/bidir={bidir}", *prob, mode=mode, bidirectional=bidir)
     run(f"{name}/costs-only", *prob, want_grad=False)
 hostile = synth_problem(4, 120, 3, 29, 30, 60, sigma=40.0)
 run("hostile/auto", *hostile)
 run("hostile/throughput", *hostile, mode="throughput8")
 run("hostile/warp (device-side log-space detour)", *hostile, mode="warp")
+run("hostile/warp32 (fp64 tier, then the log-space detour)", *hostile, mode="warp32")
+wide4 = synth_problem(15, 400, 6, 43, 30, 120, sigma=4.0)
+run("sigma4/warp32 (fp64 tier)", *wide4, mode="warp32")
 # round 2: every warp-ladder variant (NS = 2 .. 16, one and two alphabet slices), partial last chunks, blank != 0
 for L, V in ((10, 29), (40, 29), (70, 43), (100, 29), (130, 29), (170, 43), (200, 29), (250, 31)):
     prob = synth_problem(40 + L, 2 * L + 37, 2, V, L, L, blank=3)
     run(f"warp/L={L}/V={V}", *prob, mode="warp", blank=3)
+    run(f"warp32/L={L}/V={V}", *prob, mode="warp32", blank=3)
+# several label classes in one call: per-bucket SM ranges, dynamically claimed workspace slots
+mixed = synth_problem(77, 160, 64, 29, 5, 75, tmin=100)
+run("warp32/mixed classes", *mixed, mode="warp32")
+run("warp/mixed classes", *mixed, mode="warp")
 # round 2: non-blocking call, device-side cost sum, gradient scale, fused loss glue
 from aes_lac_2018_b200 import CTCLoss, sanitize_loss
 from aes_lac_2018_b200.ctc_loss import reduce_costs, _scale_gradients

@@ -18,9 +18,12 @@ def launches(path):
         d[r[mi]] = v
 
     def grp(name):
-        m = re.search(r"ctc_warp_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)>", name)
+        m = re.search(r"ctc_warp32_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", name) or re.search(r"ctc_warp32_kernel<(\d+), (\d+), (\d+), (\d+)>", name)
         if m:
-            return "ctc_warp_kernel<%s,%s,%s,%s,%s>" % m.groups(), "engine step (B=8192, warp ladder)"
+            return "ctc_warp32_kernel<%s,%s,%s,%s>" % m.groups(), "engine step (B=8192, fp32 warp ladder)"
+        m = re.search(r"ctc_warp_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", name) or re.search(r"ctc_warp_kernel<(\d+), (\d+), (\d+), (\d+), (\d+)>", name)
+        if m:
+            return "ctc_warp_kernel<%s,%s,%s,%s,%s>" % m.groups(), "fp64 second tier of the same label class (scans the bucket's status words; nothing flagged)"
         m = re.search(r"ctc_fused_kernel<(\d+), (\d+), (\d+), (\d+)>", name)
         if m:
             return "ctc_fused_kernel<%s,%s,%s,%s>" % m.groups(), "e2e pipeline chunks (B=1024 each, latency ladder)"
@@ -47,7 +50,7 @@ def launches(path):
     ncalls = max(1, thr[0] // max(1, nvar))
     lines += ["", f"engine step: {thr[0]} launches = {ncalls} engine calls x {nvar} variants;",
               f"per engine call at B=8192: {thr[1] / ncalls:.3f} ms serialised ({100 * thr[1] / tot:.1f}% of all GPU time in the run), DRAM read {thr[2] / ncalls / 1e6:.1f} MB + write {thr[3] / ncalls / 1e6:.1f} MB = {(thr[2] + thr[3]) / ncalls / 1e6:.1f} MB (algorithmic 1429.6 MB => {(thr[2] + thr[3]) / ncalls / 1429.6e6:.2f}x).",
-              "Where the extra traffic goes (per utterance-frame, NS=8, K=8): activations + gradient 232 B (algorithmic); 32-bit checkpoint column every 8 frames, written by the forward sweep and read back by the backward sweep 2 x 128 B; r image (one 128-byte row per frame) written once and read once 2 x 128 B (+ 1/s: 2 x 4 B)."]
+              "Where the extra traffic goes (per utterance-frame, NS=8, K=8): activations + gradient 232 B (algorithmic); fp32 checkpoint column + its exponent row every 8 frames, written by the forward sweep and read back by the backward sweep 2 x 144 B; p~ image (one 128-byte row per frame) written once and read once 2 x 128 B (+ 1/s: 2 x 4 B)."]
     open(os.path.join(ROOT, "profiles", "r2_launches_bench.txt"), "w").write("\n".join(lines) + "\n")
     json.dump({"dram_bytes_per_launch_set": (thr[2] + thr[3]) / ncalls, "dram_read": thr[2] / ncalls, "dram_write": thr[3] / ncalls, "algorithmic_bytes": 1429607948,
                "source": f"profiles/r2_launches_bench.txt (ncu dram__bytes_read.sum + dram__bytes_write.sum over the {nvar} variant launches of one engine call, B=8192, round-2 code)"},
@@ -88,7 +91,8 @@ def kernel(rep, name, B, T, what):
                + float(d["dram__bytes_write.sum"]) * {"Gbyte": 1e9, "Mbyte": 1e6}[u["dram__bytes_write.sum"]])
     out += ["", f"per utterance-timestep: {n / steps:.0f} warp instructions, {wf / steps:.1f} shared-memory wavefronts "
                 f"({bc / steps:.1f} of them bank-conflict replays), {traffic / steps:.0f} B of DRAM traffic (algorithmic 232 B)",
-            "(round 1, ctc_fused_kernel<8,1,8,1>: 310 instructions, 100 wavefronts (25 replays), 1016 B; profiles/r1_e_ncu_summary.txt)"]
+            "(shared-memory wavefronts include one per warp shuffle; round 2 fp64 ctc_warp_kernel<8,8,1,168,0>: 248 instructions, 55.5 wavefronts, 741 B -- profiles/r2_ncu_ns8.txt; "
+            "round 1 ctc_fused_kernel<8,1,8,1>: 310 instructions, 100 wavefronts, 1016 B -- profiles/r1_e_ncu_summary.txt)"]
     # opcode mix from the SASS page
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
