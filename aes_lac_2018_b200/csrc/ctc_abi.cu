@@ -44,7 +44,7 @@ constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBidirMaxB = 160;             // bidirectional (two sweeps + combine) path for batches up to this size ...
 constexpr size_t kBidirMaxBytes = 1u << 30;     // ... and up to this many bytes of spilled columns (B = 128, T = 1500,
                                                 // L <= 200 -- one eighth of BASELINE configs[3] -- needs 786 MB)
-constexpr int kWarpMinB = 512;              // automatic ladder choice: warp ladder from this batch size (measured crossover,
+constexpr int kWarpMinB = 640;              // automatic ladder choice: warp ladder from this batch size (measured crossover,
                                             // profiles/r2_crossover.txt)
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
 constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)

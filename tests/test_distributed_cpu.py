@@ -85,3 +85,22 @@ def test_scalar_loss_all_reduce_gloo_world2():
     want = ctc_f64.ctc_batch(acts, labels, al, ll)[0].sum()
     assert abs(res[0][1] - want) < 1e-4 * want and res[0][1] == res[1][1]
     assert abs(res[0][2] + res[1][2] - want) < 1e-4 * want
+
+
+def test_pending_loss_wait_is_idempotent():
+    """`sharded_loss_step(overlap=True)` hands the global loss back as a PendingLoss; without a process group (or after
+    the first wait) there is nothing to wait for."""
+    import torch
+    from aes_lac_2018_b200.distributed import PendingLoss
+
+    class _Work:
+        def __init__(self):
+            self.n = 0
+
+        def wait(self):
+            self.n += 1
+
+    w = _Work()
+    p = PendingLoss(torch.tensor([3.0]), w)
+    assert float(p.wait()) == 3.0 and float(p.wait()) == 3.0 and w.n == 1
+    assert float(PendingLoss(torch.tensor([1.0])).wait()) == 1.0

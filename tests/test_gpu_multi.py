@@ -36,6 +36,11 @@ def _worker(rank, world, port, q):
         assert t2.is_cuda and l2.is_cuda and not st2.any().item()
         assert abs(float(t2) - float(total)) <= 1e-5 * abs(float(total)) and abs(float(l2) - float(local)) <= 1e-5 * abs(float(local))
         assert torch.equal(g2, x.grad)
+        # ... and with the collective running beside the next step's kernels: same numbers once waited for
+        pend = [sharded_loss_step(x.detach(), lab, a, l, overlap=True)[0] for _ in range(3)]
+        for p in pend:
+            t3 = p.wait()
+            assert t3.is_cuda and float(t3) == float(t2)
         q.put((rank, float(total), float(local), x.grad.cpu().numpy(), lo, hi))
     finally:
         dist.destroy_process_group()
