@@ -543,8 +543,14 @@ ctcStatus_t run(const ctcB200Call &c)
             }
             // with an SM range the grid is full-size (CTAs outside the range retire at once, the others claim a slot)
             const int full = persistent_grid((const void *)l.v->kernel, smem_launch);
-            const int grid = (l.sm_hi > l.sm_lo) ? full : std::min(l.slots, full);
-            P.sm_lo = l.sm_lo; P.sm_hi = l.sm_hi; P.n_slots = l.slots;
+            // (CTC_B200_FLAG_SERIAL_LAUNCHES runs the buckets one after the other: no ranges then, each bucket spreads its
+            //  planned number of workers over the whole chip)
+            const bool ranged = (l.sm_hi > l.sm_lo) && !serial;
+            const int grid = ranged ? full : std::min(l.slots, full);
+            P.sm_lo = ranged ? l.sm_lo : 0; P.sm_hi = ranged ? l.sm_hi : 0; P.n_slots = l.slots;
+            if (ranged && std::getenv("CTC_B200_TEST_EMPTY_RANGES")) {
+                P.sm_lo += 100000; P.sm_hi += 100000;      // test hook: no CTA lands in its range, so the last CTA of every grid
+            }                                              // has to drain the whole bucket alone (tests/test_gpu_parity.py)
             P.queue = d_queue + 4 * li;
             l.v->kernel<<<grid, 32, smem_launch, ls>>>(P);
             if (l.v2 && !(c.flags & CTC_B200_FLAG_NO_FALLBACK)) {
@@ -554,7 +560,7 @@ ctcStatus_t run(const ctcB200Call &c)
                 if (!ensure_smem_attr((const void *)l.v2->kernel, l.smem2, st)) return st;
                 P.queue = d_queue + 4 * (kMaxLaunches / 2 + li); P.only_flagged = 1;
                 const int full2 = persistent_grid((const void *)l.v2->kernel, l.smem2);
-                const int grid2 = (l.sm_hi > l.sm_lo) ? full2 : std::min(l.slots, full2);
+                const int grid2 = ranged ? full2 : std::min(l.slots, full2);
                 l.v2->kernel<<<grid2, 32, l.smem2, ls>>>(P);
                 P.only_flagged = 0;
                 ++g_launches;

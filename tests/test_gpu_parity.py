@@ -526,3 +526,20 @@ def test_fp32_ladder_hands_wide_range_utterances_to_the_fp64_tier():
     acts, labels, al, ll = synth_problem(16, 300, 16, 29, 20, 100, sigma=6.0)
     _, _, st = ctc_loss_raw(torch.tensor(acts).cuda(), torch.tensor(labels), torch.tensor(al), torch.tensor(ll), mode="warp32", no_fallback=True)
     assert (st & 0x8).any()
+
+
+def test_sm_ranges_are_correct_for_any_cta_placement(monkeypatch):
+    """Several label classes in one call: every bucket keeps to its own range of SMs, found by reading %smid.  That is a
+    speed device, not a correctness one: whatever the block scheduler does, the last CTA of a grid to retire drains what
+    is left.  The test hook moves every range off the chip, so that NO CTA lands in its range and each bucket is done by
+    that one last CTA alone."""
+    from oracle import ctc_f64
+    acts, labels, al, ll = synth_problem(91, 150, 48, 29, 5, 120, tmin=90)
+    oc, og = ctc_f64.ctc_batch(acts, labels, al, ll)
+    for mode in ("warp32", "warp"):
+        c0, g0, s0 = _engine(acts, labels, al, ll, 0, mode)
+        monkeypatch.setenv("CTC_B200_TEST_EMPTY_RANGES", "1")
+        c1, g1, s1 = _engine(acts, labels, al, ll, 0, mode)
+        monkeypatch.delenv("CTC_B200_TEST_EMPTY_RANGES")
+        _assert_close(c1, g1, oc, og, f"empty-ranges/{mode}")
+        assert np.array_equal(c0, c1) and np.array_equal(g0, g1) and np.array_equal(s0, s1), mode
