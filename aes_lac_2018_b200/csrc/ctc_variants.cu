@@ -42,7 +42,7 @@ static const Variant kTable[] = {
 #ifdef CTC_WARP32_TABLE_INC        // kernel experiments: the table comes from a file (tools/build_alt.sh)
 #include CTC_WARP32_TABLE_INC
 #else
-    VF_(2, 8, 96), VF_(4, 8, 96), VF_(6, 8, 128), VF_(8, 8, 128), VF_(10, 8, 128), VF_(12, 8, 168), VF_(14, 8, 168), VF_(16, 8, 168),
+    VF_(2, 16, 128), VF_(4, 8, 96), VF_(6, 8, 128), VF_(8, 8, 128), VF_(10, 8, 128), VF_(12, 8, 168), VF_(14, 8, 168), VF_(16, 8, 168),
 #endif
 #else
     // latency: more warps per utterance, fewer states per thread

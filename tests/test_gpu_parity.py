@@ -543,3 +543,15 @@ def test_sm_ranges_are_correct_for_any_cta_placement(monkeypatch):
         monkeypatch.delenv("CTC_B200_TEST_EMPTY_RANGES")
         _assert_close(c1, g1, oc, og, f"empty-ranges/{mode}")
         assert np.array_equal(c0, c1) and np.array_equal(g0, g1) and np.array_equal(s0, s1), mode
+
+
+def test_serial_launches_give_the_same_numbers():
+    """CTC_B200_FLAG_SERIAL_LAUNCHES keeps every kernel of a call on the caller's stream (no forked streams, no SM ranges)."""
+    from aes_lac_2018_b200 import ctc_loss_raw
+    acts, labels, al, ll = synth_problem(92, 140, 40, 29, 5, 110, tmin=100)
+    a = torch.tensor(acts).cuda()
+    args = [torch.tensor(x) for x in (labels, al, ll)]
+    for mode in ("warp32", "warp", "throughput8"):
+        c0, g0, s0 = ctc_loss_raw(a, *args, mode=mode)
+        c1, g1, s1 = ctc_loss_raw(a, *args, mode=mode, serial_launches=True)
+        assert torch.equal(c0, c1) and torch.equal(g0, g1) and torch.equal(s0, s1), mode
