@@ -315,6 +315,7 @@ struct AuxStreams {
     }
 };
 thread_local int *g_status_dev_override = nullptr;      // set by the host-buffer entry point around run()
+thread_local const int *g_labels_dev_override = nullptr; // ... labels of the slice, already on the device (uploaded once for the batch)
 thread_local AuxStreams g_aux[16];
 
 AuxStreams *aux_streams()
@@ -463,15 +464,15 @@ ctcStatus_t run(const ctcB200Call &c)
     cudaStream_t stream = (cudaStream_t)c.stream;
     char *ws = (char *)c.workspace;
     int *d_meta = (int *)(ws + plan.off_meta);
-    int *d_labels = (int *)(ws + plan.off_labels);
+    const int *d_labels = g_labels_dev_override ? g_labels_dev_override : (const int *)(ws + plan.off_labels);
     float *d_costs = c.costs_device ? c.costs_device : (float *)(ws + plan.off_costs);
     int *d_status = g_status_dev_override ? g_status_dev_override
                     : (c.status_device ? c.status_device : (int *)(ws + plan.off_status));
 
     if (!check(cudaMemcpyAsync(d_meta, plan.meta.data(), sizeof(int) * 4 * (size_t)B, cudaMemcpyHostToDevice, stream),
                "H2D metadata", CTC_STATUS_MEMOPS_FAILED, st)) return st;
-    if (plan.total_labels > 0 &&
-        !check(cudaMemcpyAsync(d_labels, c.flat_labels, sizeof(int) * (size_t)plan.total_labels, cudaMemcpyHostToDevice, stream),
+    if (plan.total_labels > 0 && !g_labels_dev_override &&
+        !check(cudaMemcpyAsync((int *)(ws + plan.off_labels), c.flat_labels, sizeof(int) * (size_t)plan.total_labels, cudaMemcpyHostToDevice, stream),
                "H2D labels", CTC_STATUS_MEMOPS_FAILED, st)) return st;
 
     FusedParams P;
@@ -614,7 +615,8 @@ ctcStatus_t run(const ctcB200Call &c)
 // ---- host-buffer entry point: chunked H2D -> kernels -> D2H pipeline -----------------------------
 struct HostPlan {
     int n_chunks = 1, n_buf = 1, Bc = 0;
-    size_t inner_ws = 0, acts_bytes = 0, off_costs = 0, off_status = 0, off_sets = 0, set_bytes = 0, total = 0;
+    size_t inner_ws = 0, acts_bytes = 0, off_costs = 0, off_status = 0, off_labels = 0, off_sets = 0, set_bytes = 0, total = 0;
+    long long total_labels = 0;
 };
 
 ctcStatus_t make_host_plan(const int *label_lengths, const int *input_lengths, int V, int B, int T, bool want_grad,
@@ -639,6 +641,9 @@ ctcStatus_t make_host_plan(const int *label_lengths, const int *input_lengths, i
     size_t o = 0;
     hp.off_costs = o;  o = align_up(o + sizeof(float) * (size_t)B, 256);
     hp.off_status = o; o = align_up(o + sizeof(int) * (size_t)B, 256);
+    hp.total_labels = 0;
+    for (int b = 0; b < B; ++b) hp.total_labels += std::max(label_lengths[b], 0);
+    hp.off_labels = o; o = align_up(o + sizeof(int) * (size_t)std::max<long long>(hp.total_labels, 1), 256);
     hp.off_sets = o;
     hp.set_bytes = hp.acts_bytes * (want_grad ? 2 : 1) + align_up(hp.inner_ws, 256);
     hp.total = o + hp.set_bytes * hp.n_buf + 256;
@@ -679,6 +684,15 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
     if (!check(cudaEventRecord(aux->pipe_fork, stream), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
     for (int i = 0; i < kPipeStreams; ++i)
         if (!check(cudaStreamWaitEvent(aux->pipe[i], aux->pipe_fork, 0), "stream wait", CTC_STATUS_EXECUTION_FAILED, st)) return st;
+    // The labels of the whole batch go up ONCE, first thing on the copy-in stream.  A per-slice upload on the kernel
+    // stream (what the inner call does on its own) sits in the H2D engine's queue waiting for that stream's events --
+    // the download of an earlier slice -- and the activation uploads of the next slices queue behind it: with pinned
+    // label arrays that head-of-line blocking cost 6 ms of a 25 ms step (pageable label arrays are copied inline and
+    // never showed it).
+    int *d_labels_all = (int *)(ws + hp.off_labels);
+    if (hp.total_labels > 0 &&
+        !check(cudaMemcpyAsync(d_labels_all, c.flat_labels, sizeof(int) * (size_t)hp.total_labels, cudaMemcpyHostToDevice, s_in),
+               "H2D labels", CTC_STATUS_MEMOPS_FAILED, st)) return st;
     const size_t row_all = sizeof(float) * (size_t)B * V;
     for (int ch = 0; ch < hp.n_chunks; ++ch) {
         const int lo = ch * hp.Bc, n = std::min(hp.Bc, B - lo);
@@ -712,8 +726,10 @@ ctcStatus_t run_host(const ctcB200HostCall &c)
         k.stream = (CUstream)s_k;
         k.flags = (c.flags & 0x700u) | CTC_B200_FLAG_NO_SYNC;
         g_status_dev_override = d_status + lo;
+        g_labels_dev_override = d_labels_all + lab_off[ch];
         st = run(k);
         g_status_dev_override = nullptr;
+        g_labels_dev_override = nullptr;
         if (st != CTC_STATUS_SUCCESS) return st;
         if (!check(cudaEventRecord(aux->ev_k[ch], s_k), "event record", CTC_STATUS_EXECUTION_FAILED, st)) return st;
         // copy-out
