@@ -555,3 +555,24 @@ def test_serial_launches_give_the_same_numbers():
         c0, g0, s0 = ctc_loss_raw(a, *args, mode=mode)
         c1, g1, s1 = ctc_loss_raw(a, *args, mode=mode, serial_launches=True)
         assert torch.equal(c0, c1) and torch.equal(g0, g1) and torch.equal(s0, s1), mode
+
+
+def test_fp32_ladder_call_options():
+    """The options the drop-in and the loss glue use, on the throughput ladder explicitly (small batches take the latency
+    ladder by default): strided B x T x V storage read through a transposed view, a folded gradient scale, blank != 0,
+    a two-slice alphabet, costs only."""
+    from aes_lac_2018_b200 import ctc_loss_raw
+    from oracle import ctc_f64
+    for V, blank in ((29, 3), (43, 0), (63, 62)):
+        acts, labels, al, ll = synth_problem(93 + V, 130, 24, V, 0, 100, tmin=60, blank=blank)
+        oc, og = ctc_f64.ctc_batch(acts, labels, al, ll, blank)
+        btv = torch.tensor(np.ascontiguousarray(acts.transpose(1, 0, 2))).cuda()      # B x T x V storage
+        view = btv.transpose(0, 1)                                                      # T x B x V view, strides (V, T*V, 1)
+        assert not view.is_contiguous()
+        args = [torch.tensor(x) for x in (labels, al, ll)]
+        for mode in ("warp32", "warp"):
+            c, g, st = ctc_loss_raw(view, *args, blank=blank, mode=mode, grad_scale=0.37)
+            _assert_close(c.numpy().astype(np.float64), g.cpu().numpy().astype(np.float64) / 0.37, oc, og, f"options/{mode}/V{V}")
+            assert not (st & 0x18).any()
+            c2, g2, _ = ctc_loss_raw(view, *args, blank=blank, mode=mode, want_grad=False)
+            assert g2 is None and torch.equal(c2, c), mode

@@ -26,7 +26,7 @@ def launches(path):
             return "ctc_warp_kernel<%s,%s,%s,%s,%s>" % m.groups(), "fp64 second tier of the same label class (scans the bucket's status words; nothing flagged)"
         m = re.search(r"ctc_fused_kernel<(\d+), (\d+), (\d+), (\d+)>", name)
         if m:
-            return "ctc_fused_kernel<%s,%s,%s,%s>" % m.groups(), "e2e pipeline chunks (B=1024 each, latency ladder)"
+            return "ctc_fused_kernel<%s,%s,%s,%s>" % m.groups(), "e2e pipeline slices (256 utterances each, latency ladder)"
         for key, role in (("ctc_logspace", "device-side log-space detour (scans the status words; nothing flagged)"),
                           ("reduce_costs", "device-side cost sum (operand of the scalar all-reduce)"),
                           ("scale_gradients", "gradient scale"), ("ctc_combine", "bidirectional second half")):
