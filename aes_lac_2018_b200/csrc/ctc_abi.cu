@@ -44,10 +44,10 @@ constexpr int kMaxSmem = 227 * 1024;
 constexpr int kBidirMaxB = 160;             // bidirectional (two sweeps + combine) path for batches up to this size ...
 constexpr size_t kBidirMaxBytes = 1u << 30;     // ... and up to this many bytes of spilled columns (B = 128, T = 1500,
                                                 // L <= 200 -- one eighth of BASELINE configs[3] -- needs 786 MB)
-constexpr int kWarpMinB = 640;              // automatic ladder choice: warp ladder from this batch size (measured crossover,
-                                            // profiles/r2_crossover.txt)
+constexpr int kWarpMinB = 640;              // automatic ladder choice: fp32 warp ladder from this batch size (measured
+                                            // crossover at T = 750: 0.52 / 0.52 ms at B = 512, 0.59 / 0.87 ms at B = 768;
+                                            // profiles/r2_crossover_w32.txt)
 constexpr int kWarpMaxLabelLen = 255;       // NS = 16: 512 states hold 2L + 2
-constexpr int kWarpSlotCap = 4096;          // upper bound on persistent CTAs per launch (148 SMs x <= 27 warps)
 constexpr int kMaxLaunches = 32;            // queue counters: launches of one call (fp32 ladder: first and second tier)
 
 const Variant *ladder_table(int ladder, int vch, int *n)
@@ -120,8 +120,9 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
     // mode: 0 auto, 1 throughput ladder (16-step chunks), 2 latency ladder, 3 throughput ladder (8-step chunks),
     // 4 warp ladder (ctc_warp.cuh: one warp per utterance, register-resident, persistent CTAs),
     // 5 fp32 warp ladder (ctc_warp32.cuh: the same organisation, single-precision recursion with per-lane exponents).
-    // Auto (measured on B200, T=750, L~U{50..200}; profiles/): below ~2000 utterances the GPU is not full with one
-    // warp per utterance, so spend more warps per utterance (latency ladder); above, the warp ladder wins.
+    // Auto (measured on B200, T=750, L~U{50..200}; profiles/r2_crossover_w32.txt): below kWarpMinB utterances the GPU is
+    // far from full with one warp per utterance, so spend more warps per utterance (latency ladder); above, the fp32
+    // warp ladder wins.
     int vch = (V + 31) / 32;
     if (vch > kMaxVch)
         return fail(CTC_STATUS_UNKNOWN_ERROR, "alphabet_size above 64 is not supported by this build");
@@ -199,7 +200,7 @@ ctcStatus_t make_plan(const int *label_lengths, const int *input_lengths, int V,
         // per CTA: nC checkpoint columns (SP doubles each) followed by nC p~ images
         l.slots = l.count;
         if (v->warp) {                                   // per resident CTA: 32-bit checkpoints, r images, 1/s
-            l.slots = std::min(l.count, kWarpSlotCap);
+            l.slots = l.count;                            // (cut down to the resident warps below)
             long long words = v->slot_words(T_max);
             if (v->warp >= 3) {                          // second tier: the fp64 warp variant of the same NS shares the slots
                 int n2 = 0;
