@@ -730,6 +730,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp_kernel(const FusedParams P)
         for (int t = T; t < P.T_max; ++t)
             for (int k = lane; k < V; k += 32) grads_b[(long long)t * gst + k] = 0.f;
         dbg_out();
+        if (P.debug && lane == 0) P.debug[b * 16 + 4] = __float_as_uint(chk_dev);   // (what the range self-check saw)
     }
     if (P.sm_hi > P.sm_lo && lane == 0) atomicAdd(P.queue + 1, 1);
 }
