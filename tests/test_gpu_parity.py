@@ -576,3 +576,40 @@ def test_fp32_ladder_call_options():
             assert not (st & 0x18).any()
             c2, g2, _ = ctc_loss_raw(view, *args, blank=blank, mode=mode, want_grad=False)
             assert g2 is None and torch.equal(c2, c), mode
+
+
+def _torch_f64_on_gpu(d_acts, labels, al, ll, blank=0):
+    """An independent float64 implementation run on the device: torch.nn.functional.ctc_loss on log_softmax of the
+    float64 activations, per-utterance costs and d(sum of costs) / d(activations) by autograd.  It is the same function
+    that pins oracle/ctc_f64.py (tests/golden/make_golden.py, agreement 1e-12); on the GPU it can check EVERY utterance
+    of a BASELINE-sized batch, where the numpy oracle does spot checks."""
+    import torch.nn.functional as F
+    x = d_acts.double().requires_grad_()
+    costs = F.ctc_loss(F.log_softmax(x, -1), labels.long().cuda(), al.long(), ll.long(), blank=blank, reduction="none", zero_infinity=False)
+    costs.sum().backward()
+    return costs.detach().cpu().numpy(), x.grad
+
+
+@pytest.mark.parametrize("shape", ["configs3_b1024_t1500", "bench_b2048_t750", "bench_b8192_t750"])
+def test_every_utterance_of_a_full_size_batch_against_torch_float64(shape):
+    """BASELINE configs[3] literally (B = 1024, T = 1500), a quarter of the bench batch and the bench batch itself
+    (B = 2048 / 8192, T = 750), V = 29, L ~ U{50..200}: all utterances, all frames, against float64 torch on the same
+    device (~25 GB for its alpha table at B = 8192), on the default path (fp32 warp ladder) and on the fp64 warp ladder."""
+    from aes_lac_2018_b200 import ctc_loss_raw
+    B, T = {"configs3_b1024_t1500": (1024, 1500), "bench_b2048_t750": (2048, 750), "bench_b8192_t750": (8192, 750)}[shape]
+    V = 29
+    g = torch.Generator().manual_seed(99)
+    acts = torch.randn(T, B, V, generator=g)
+    ll = torch.randint(50, 201, (B,), generator=g, dtype=torch.int32)
+    al = torch.full((B,), T, dtype=torch.int32)
+    labels = torch.randint(1, V, (int(ll.sum()),), generator=g, dtype=torch.int32)
+    d_acts = acts.cuda()
+    want_c, want_g = _torch_f64_on_gpu(d_acts, labels, al, ll)
+    for mode in ("auto", "warp"):
+        costs, grads, status = ctc_loss_raw(d_acts, labels, al, ll, mode=mode)
+        assert not status.any(), mode
+        rel = np.abs(costs.numpy().astype(np.float64) - want_c) / np.maximum(1.0, np.abs(want_c))
+        err = float((grads.double() - want_g).abs().max().item())
+        assert rel.max() <= LOSS_RTOL and err <= GRAD_ATOL, (mode, rel.max(), err)
+    del want_g
+    torch.cuda.empty_cache()
