@@ -42,7 +42,13 @@ static const Variant kTable[] = {
 #ifdef CTC_WARP32_TABLE_INC        // kernel experiments: the table comes from a file (tools/build_alt.sh)
 #include CTC_WARP32_TABLE_INC
 #else
+    // register caps measured per label class (profiles/r2_w32_variants.txt); the two-slice alphabets (V = 32 .. 63, e.g. the
+    // PT-BR alphabet of BASELINE configs[2]) hold twice the row registers and want more room at NS = 4, 10, 16
+#if CTC_VCH == 1
     VF_(2, 16, 128), VF_(4, 8, 96), VF_(6, 8, 128), VF_(8, 8, 128), VF_(10, 8, 128), VF_(12, 8, 168), VF_(14, 8, 168), VF_(16, 8, 168),
+#else
+    VF_(2, 16, 128), VF_(4, 8, 128), VF_(6, 8, 128), VF_(8, 8, 128), VF_(10, 8, 168), VF_(12, 8, 168), VF_(14, 8, 168), VF_(16, 8, 224),
+#endif
 #endif
 #else
     // latency: more warps per utterance, fewer states per thread
