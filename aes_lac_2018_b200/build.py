@@ -18,7 +18,7 @@ LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libctc_b200.so")
 N_GROUPS = 10
 HEADERS = ["ctc_fused.cuh", "ctc_warp.cuh", "ctc_warp32.cuh", "ctc_logspace.cuh", "ctc_decode.cuh", "ctc_combine.cuh", "ctc_editdist.cuh", "ctc_variants.h",
-           "ctc_variants.cu", "ctc_abi.cu", "ctc_head.cu", "ctc_head_tc.cuh", "ctc_internal.h", os.path.join(ROOT, "include", "ctc.h")]
+           "ctc_variants.cu", "ctc_abi.cu", "ctc_head.cu", "ctc_head_tc.cuh", "ctc_head_bwd_tc.cuh", "ctc_internal.h", os.path.join(ROOT, "include", "ctc.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -34,11 +34,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/ctc.h"
 #include "ctc_internal.h"
 #include "ctc_head_tc.cuh"
+#include "ctc_head_bwd_tc.cuh"
 
 namespace ctcb200 {
 
@@ -419,7 +421,7 @@ size_t up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
 struct HeadLayout {
     int VP, RB, rows_per_block;
-    size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, off_bc, total;
+    size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, off_bc, off_wtc, total;
 };
 
 HeadLayout head_layout(int N, int H, int V)
@@ -427,9 +429,9 @@ HeadLayout head_layout(int N, int H, int V)
     HeadLayout l;
     l.VP = (V <= 32) ? 32 : 64;
     const int tiles = (H + 127) / 128;
-    int rb = std::max(1, (8 * 148 + tiles - 1) / tiles);   // about eight CTAs per SM for the weight-gradient pass
+    int rb = std::max(1, (4 * 148 + tiles - 1) / tiles);   // two waves of two resident CTAs per SM for the weight-gradient pass
     int rows = (N + rb - 1) / rb;
-    rows = std::max(16, (rows + 15) / 16 * 16);
+    rows = std::max(32, (rows + 31) / 32 * 32);
     l.rows_per_block = rows;
     l.RB = (N + rows - 1) / rows;
     size_t o = 0;
@@ -443,6 +445,7 @@ HeadLayout head_layout(int N, int H, int V)
     l.off_invstd = o; o += up(sizeof(float) * H);
     l.off_part = o;   o += up(sizeof(float) * (size_t)l.RB * l.VP * H);
     l.off_bc = o;     o += up(tc::head_tc_weight_bytes(H, l.VP));
+    l.off_wtc = o;    o += up(tc::head_dgrad_tc_weight_bytes(H, l.VP));
     l.total = o;
     return l;
 }
@@ -552,16 +555,29 @@ ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *c)
         const int rows = (N + ctas - 1) / ctas;
         head_colsum_kernel<<<(N + rows - 1) / rows, 256, 0, s>>>(c->dlogits, N, V, rows, sv);
     }
+    // CTC_B200_HEAD_FMA=1: the round-1 fp32-FMA backward kernels (A/B timing and debugging only)
+    static const bool fma_path = std::getenv("CTC_B200_HEAD_FMA") != nullptr;
     const dim3 gw((H + 127) / 128, l.RB);
-    if (l.VP == 32) head_wgrad_kernel<32><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
-    else head_wgrad_kernel<64><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+    if (fma_path) {
+        if (l.VP == 32) head_wgrad_kernel<32><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+        else head_wgrad_kernel<64><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+    } else {
+        const int smem = tc::head_wgrad_tc_smem_bytes(l.VP);
+        if (l.VP == 32) {
+            if (!ok(cudaFuncSetAttribute(tc::head_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
+            tc::head_wgrad_tc_kernel<32><<<gw, 256, smem, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+        } else {
+            if (!ok(cudaFuncSetAttribute(tc::head_wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
+            tc::head_wgrad_tc_kernel<64><<<gw, 256, smem, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
+        }
+    }
     head_reduce_kernel<<<dim3((H + 127) / 128, V), 128, 0, s>>>(part, l.RB, l.VP, sv, H, c->bn_weight, c->bn_bias,
                                                                 c->save_invstd, c->dweight);
     head_finalize_kernel<<<(H + 127) / 128, 128, 0, s>>>(part, sv, N, H, V, c->weight, c->bn_weight, c->save_mean,
                                                         c->save_invstd, c->training, c->dbn_weight, c->dbn_bias, coef);
     ctcb200_count_launch();
     ctcb200_count_launch(); ctcb200_count_launch(); ctcb200_count_launch();
-    if (c->dx) {
+    if (c->dx && fma_path) {
         const int tiles = (H + 127) / 128, nblk = (N + 63) / 64;
         const int groups = std::max(1, std::min(nblk, (148 * 6 + tiles - 1) / tiles));    // ~6 CTAs per SM in flight
         const int bpc = (nblk + groups - 1) / groups;
@@ -569,6 +585,23 @@ ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *c)
         if (l.VP == 32) head_dgrad_kernel<32><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V, bpc);
         else head_dgrad_kernel<64><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V, bpc);
         ctcb200_count_launch();
+    } else if (c->dx) {
+        float4 *wtc = (float4 *)(ws + l.off_wtc);
+        const int tiles = (H + tc::kDBM - 1) / tc::kDBM, nblk = (N + tc::kDBN - 1) / tc::kDBN;
+        tc::head_wt_tc_kernel<<<(tiles * (l.VP / 4) * tc::kDBM + 127) / 128, 128, 0, s>>>(c->weight, H, V, l.VP, wtc);
+        const int resident = (l.VP == 32) ? 2 : 1;
+        const int groups = std::max(1, std::min(nblk, (148 * resident * 2 + tiles - 1) / tiles));   // two waves of resident CTAs
+        const int bpc = (nblk + groups - 1) / groups;
+        const dim3 gd(tiles, (nblk + bpc - 1) / bpc);
+        const int smem = tc::head_dgrad_tc_smem_bytes(l.VP);
+        if (l.VP == 32) {
+            if (!ok(cudaFuncSetAttribute(tc::head_dgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
+            tc::head_dgrad_tc_kernel<32><<<gd, 256, smem, s>>>(c->x, c->dlogits, wtc, coef, c->dx, N, H, V, bpc);
+        } else {
+            if (!ok(cudaFuncSetAttribute(tc::head_dgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
+            tc::head_dgrad_tc_kernel<64><<<gd, 256, smem, s>>>(c->x, c->dlogits, wtc, coef, c->dx, N, H, V, bpc);
+        }
+        ctcb200_count_launch(); ctcb200_count_launch();
     }
     if (!ok(cudaGetLastError(), "head backward launch", st)) return st;
     return CTC_STATUS_SUCCESS;
