@@ -38,13 +38,6 @@ __device__ __forceinline__ float ldg_stream(const float *p)
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float4 ldg_stream4(const float *p)
-{
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -59,11 +52,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
 constexpr int kWBM = 128, kWBK = 32;                       // features per CTA, rows per stage
 constexpr int kWPF = 4;                                    // register-staged tiles in flight per thread
 __host__ __device__ inline int head_wgrad_tc_smem_bytes(int VP) { return 2 * (2 * kWBM * kWBK * 4 + 2 * VP * kWBK * 4) + 1024; }
-// matrix descriptor of a swizzled operand tile (layout type at bits [61,64): 1 = 128-byte swizzle with 32-byte atoms)
-__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
-{
-    return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)layout_type << 61);
-}
 
 template <int VP>
 __global__ void __launch_bounds__(256, 2) head_wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl,

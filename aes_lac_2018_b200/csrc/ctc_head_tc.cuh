@@ -10,11 +10,12 @@
 // -- three MMAs per K-step, still far below the HBM time of the tile.
 //
 // One CTA = 128 rows of x (UMMA M = 128, cta_group::1), N = VP columns, accumulator = VP TMEM columns.
-// The operands cannot come straight from HBM by TMA: x needs (x - mu) and the hi/lo split first.  So the 128 threads
-// load the 128 x 32 tile of a stage into registers (8 float4 each, sector-aligned), transform it, and store a_hi and
-// a_lo to shared memory in the canonical K-major SWIZZLE_NONE UMMA layout (core matrix = 8 rows x 16 bytes; here
-// 16-byte column c of the tile holds its 128 rows contiguously => LBO = 2048 B between the two K-halves of an MMA,
-// SBO = 128 B between 8-row groups).  256 threads: 4 float4 of a tile each.  The weights arrive pre-split and pre-arranged in that layout (head_fold_tc_kernel).
+// The operands cannot come straight from HBM by TMA: x needs (x - mu) and the hi/lo split first.  So the 256 threads
+// load the 128 x 32 tile of a stage into registers (4 float4 each; a quarter-warp takes the 128 contiguous bytes a row
+// has in the tile), transform it, and store a_hi and a_lo to shared memory in the K-major SWIZZLE_128B UMMA layout (row
+// = 128 bytes = the 32 features of the tile, 16-byte chunk c of row r at chunk c ^ (r & 7), groups of 8 rows 1024 bytes
+// apart = SBO; the K = 8 steps of an MMA advance the start address by 32 bytes inside the swizzled row).  The weights
+// arrive pre-split and pre-arranged in that layout (head_fold_tc_kernel).
 // Two stages: while the tensor core works on stage s (tracked by an mbarrier through tcgen05.commit) the threads
 // transform stage s^1 and the global loads of the stage after are in flight in registers.
 // Epilogue: each warp reads its 32 TMEM lanes (tcgen05.ld 32x32b: one full logits row per thread), adds the bias,
@@ -85,14 +86,27 @@ constexpr int kPF = 4;                                    // register-staged til
 constexpr int kThreads = 256;                             // 8 warps: all of them load / transform, warps 0-3 run the epilogue
 constexpr int kXPT = kBM * kBK / 4 / kThreads;            // float4 of a tile per thread (4)
 
-__host__ __device__ inline int head_tc_smem_bytes(int VP) { return 2 * (2 * kBM * kBK * 4 + 2 * VP * kBK * 4); }
+__host__ __device__ inline int head_tc_smem_bytes(int VP) { return 2 * (2 * kBM * kBK * 4 + 2 * VP * kBK * 4) + 1024; }
 __host__ __device__ inline size_t head_tc_weight_bytes(int H, int VP)
 {
     return (size_t)((H + kBK - 1) / kBK) * 2 * kBK * VP * 4;
 }
+// matrix descriptor of a swizzled operand tile (layout type at bits [61,64): 2 = 128-byte swizzle, 1 = 128-byte swizzle
+// with 32-byte atoms)
+__device__ __forceinline__ uint64_t smem_desc_sw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type)
+{
+    return smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ float4 ldg_stream4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 
 // weights, already scaled by gamma * invstd (wk[h][v], head_fold_kernel), split into tf32 hi/lo and laid out as the
-// K-major canonical tiles the MMA reads: tile kt, part (0 hi, 1 lo), 16-byte column c, row n -> float4 of k = kt*32+c*4..+3
+// K-major SWIZZLE_128B tiles the MMA reads: tile kt, part (0 hi, 1 lo), class row n = 128 bytes (the 32 features of the
+// tile), 16-byte chunk c of row n stored at chunk c ^ (n & 7)
 __global__ void head_fold_tc_kernel(const float *__restrict__ wk, int H, int VP, float4 *__restrict__ bc)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,21 +121,23 @@ __global__ void head_fold_tc_kernel(const float *__restrict__ wk, int H, int VP,
         hi[e] = __uint_as_float(tf32_rna(w));
         lo[e] = __uint_as_float(tf32_rna(w - hi[e]));
     }
-    bc[((size_t)(kt * 2 + 0) * 8 + c) * VP + n] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    bc[((size_t)(kt * 2 + 1) * 8 + c) * VP + n] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    bc[((size_t)(kt * 2 + 0) * VP + n) * 8 + (c ^ (n & 7))] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    bc[((size_t)(kt * 2 + 1) * VP + n) * 8 + (c ^ (n & 7))] = make_float4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 template <int VP>
-__global__ void __launch_bounds__(kThreads) head_fwd_tc_kernel(const float *__restrict__ x, const float4 *__restrict__ bc,
-                                                          const float *__restrict__ bias, const float *__restrict__ mean,
-                                                          float *__restrict__ out, int N, int H, int V, int softmax)
+__global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *__restrict__ x, const float4 *__restrict__ bc,
+                                                             const float *__restrict__ bias, const float *__restrict__ mean,
+                                                             float *__restrict__ out, int N, int H, int V, int softmax)
 {
     constexpr int A_F4 = kBM * kBK / 4;                    // float4 per A tile (one of hi / lo)
     constexpr int B_F4 = VP * kBK / 4;
-    extern __shared__ __align__(1024) unsigned char hsm[];
+    extern __shared__ __align__(1024) unsigned char hsm_raw[];
     __shared__ __align__(8) uint64_t mbar[3];              // [0], [1]: stage free again; [2]: accumulator complete
     __shared__ uint32_t tmem_base_s;
     constexpr int STAGE_F4 = 2 * A_F4 + 2 * B_F4;          // stage s: [a_hi | a_lo | b_hi | b_lo]
+    // (the swizzle is a function of absolute shared-memory address bits: every operand tile starts on a 1024-byte line)
+    unsigned char *const hsm = hsm_raw + ((1024u - (smem_u32(hsm_raw) & 1023u)) & 1023u);
     float4 *const stage0 = (float4 *)hsm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n0 = blockIdx.x * kBM;
@@ -141,26 +157,28 @@ __global__ void __launch_bounds__(kThreads) head_fwd_tc_kernel(const float *__re
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
 
-    // kPF register buffers: the loads of tile kt+kPF are issued right after tile kt has been transformed, so kPF tiles
-    // (64 KB per CTA, two CTAs per SM) are in flight while the threads transform and the tensor core multiplies.
-    // this thread's kXPT float4 of a tile: row warp*16 + lane/2, 16-byte columns i*2 + (lane & 1)
-    // (two lanes cover one 32-byte sector of a row; 16 consecutive rows per instruction -> conflict-free 16-byte stores)
-    auto gload = [&](int kt, float4 (&xr)[kXPT]) {
+    // A quarter-warp loads the 128 bytes one row has in a tile (32 features) and stores them as the 8 chunks of that row's
+    // swizzled line: coalesced 128-byte global segments, conflict-free 16-byte stores.  This thread: chunk h4l of rows
+    // i*32 + warp*4 + rq, i = 0..3  (round 1 loaded 32-byte pieces of 16 rows per instruction: 61 % L1 throughput, the
+    // x stream at 24 % of the DRAM peak)
+    const int h4l = lane & 7, rq = lane >> 3;
+    const int rl = warp * 4 + rq;                          // row of the thread inside a group of 32
+    const int aoff = rl * 8 + (h4l ^ (rl & 7));            // float4 slot; + i * 256 for the group
+    auto gload = [&](int kt, float4 (&xr)[kXPT], float4 &mu) {
+        const int k = kt * kBK + h4l * 4;
 #pragma unroll
         for (int i = 0; i < kXPT; ++i) {
-            const int r = warp * 16 + (lane >> 1), c = i * 2 + (lane & 1);
-            const int n = n0 + r, k = kt * kBK + c * 4;
-            xr[i] = (n < N && k < H) ? __ldg((const float4 *)(x + (size_t)n * H + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = n0 + i * 32 + rl;
+            xr[i] = (n < N && k < H) ? ldg_stream4(x + (size_t)n * H + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        mu = (k < H) ? __ldg((const float4 *)(mean + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(VP >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     constexpr int BQ = (B_F4 + kThreads - 1) / kThreads;   // weight float4 per thread and part
-
-    auto stage_body = [&](int kt, float4 (&xr)[kXPT]) {
-        const int s = kt & 1;
-        float4 *const Ahi = stage0 + s * STAGE_F4, *const Alo = Ahi + A_F4, *const Bhi = Alo + A_F4, *const Blo = Bhi + B_F4;
-        float4 bq[2 * BQ];                                 // weight tile (L2-resident): requested first, stored last
+    // the weight tile (L2-resident) of a stage is requested one stage ahead: its L2 round trip sat exposed between the
+    // transform and the MMAs of every stage in round 1
+    auto wload = [&](int kt, float4 (&bq)[2 * BQ]) {
 #pragma unroll
         for (int q = 0; q < BQ; ++q) {
             if (tid + q * kThreads < B_F4) {
@@ -168,20 +186,21 @@ __global__ void __launch_bounds__(kThreads) head_fwd_tc_kernel(const float *__re
                 bq[BQ + q] = __ldg(bc + (size_t)(kt * 2 + 1) * B_F4 + tid + q * kThreads);
             }
         }
+    };
+
+    auto stage_body = [&](int kt, float4 (&xr)[kXPT], float4 &mu, float4 (&bq)[2 * BQ], float4 (&bnext)[2 * BQ]) {
+        const int s = kt & 1;
+        float4 *const Ahi = stage0 + s * STAGE_F4, *const Alo = Ahi + A_F4, *const Bhi = Alo + A_F4, *const Blo = Bhi + B_F4;
+        if (kt + 1 < nk) wload(kt + 1, bnext);
         if (kt >= 2) mbar_wait(&mbar[s], (uint32_t)(((kt >> 1) - 1) & 1));     // the MMAs of tile kt-2 have read stage s
 #pragma unroll
         for (int i = 0; i < kXPT; ++i) {
-            const int r = warp * 16 + (lane >> 1), c = i * 2 + (lane & 1);
-            const int k = kt * kBK + c * 4;
-            float4 mu = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < H) mu = __ldg((const float4 *)(mean + k));
             const float v0 = xr[i].x - mu.x, v1 = xr[i].y - mu.y, v2 = xr[i].z - mu.z, v3 = xr[i].w - mu.w;
             const float h0 = __uint_as_float(tf32_rna(v0)), h1 = __uint_as_float(tf32_rna(v1));
             const float h2 = __uint_as_float(tf32_rna(v2)), h3 = __uint_as_float(tf32_rna(v3));
-            Ahi[c * kBM + r] = make_float4(h0, h1, h2, h3);
-            Alo[c * kBM + r] = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3);      // exact in fp32; the MMA reads its top 19 bits
+            Ahi[aoff + i * 256] = make_float4(h0, h1, h2, h3);
+            Alo[aoff + i * 256] = make_float4(v0 - h0, v1 - h1, v2 - h2, v3 - h3);      // exact in fp32; the MMA reads its top 19 bits
         }
-        if (kt + kPF < nk) gload(kt + kPF, xr);            // (this buffer is free again)
 #pragma unroll
         for (int q = 0; q < BQ; ++q) {
             if (tid + q * kThreads < B_F4) {
@@ -189,16 +208,18 @@ __global__ void __launch_bounds__(kThreads) head_fwd_tc_kernel(const float *__re
                 Blo[tid + q * kThreads] = bq[BQ + q];
             }
         }
+        if (kt + kPF < nk) gload(kt + kPF, xr, mu);        // (this buffer is free again)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> visible to the MMA
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi), bl = smem_u32(Blo);
 #pragma unroll
-            for (int j = 0; j < kBK / 8; ++j) {            // one MMA covers K = 8 tf32 = two 16-byte columns
-                const uint32_t ao = j * 2 * kBM * 16, bo = j * 2 * VP * 16;
-                const uint64_t dah = smem_desc(ah + ao, kBM * 16, 128), dal = smem_desc(al + ao, kBM * 16, 128);
-                const uint64_t dbh = smem_desc(bh + bo, VP * 16, 128), dbl = smem_desc(bl + bo, VP * 16, 128);
+            for (int j = 0; j < kBK / 8; ++j) {            // one MMA covers K = 8 tf32 = 32 bytes inside the 128-byte swizzled rows
+                const uint32_t o = j * 32;
+                // K-major SWIZZLE_128B: SBO = 1024 B between groups of 8 rows; LBO is not used
+                const uint64_t dah = smem_desc_sw(ah + o, 16, 1024, 2), dal = smem_desc_sw(al + o, 16, 1024, 2);
+                const uint64_t dbh = smem_desc_sw(bh + o, 16, 1024, 2), dbl = smem_desc_sw(bl + o, 16, 1024, 2);
                 mma_tf32(tmem, dal, dbh, idesc, (kt > 0 || j > 0) ? 1u : 0u);   // small terms first
                 mma_tf32(tmem, dah, dbl, idesc, 1u);
                 mma_tf32(tmem, dah, dbh, idesc, 1u);
@@ -208,16 +229,18 @@ __global__ void __launch_bounds__(kThreads) head_fwd_tc_kernel(const float *__re
         }
     };
 
-    float4 xa[kXPT], xb[kXPT], xc[kXPT], xd[kXPT];
-    gload(0, xa);
-    if (nk > 1) gload(1, xb);
-    if (nk > 2) gload(2, xc);
-    if (nk > 3) gload(3, xd);
+    float4 xa[kXPT], xb[kXPT], xc[kXPT], xd[kXPT], ma, mb, mc, md;
+    float4 bA[2 * BQ], bB[2 * BQ];
+    gload(0, xa, ma);
+    wload(0, bA);
+    if (nk > 1) gload(1, xb, mb);
+    if (nk > 2) gload(2, xc, mc);
+    if (nk > 3) gload(3, xd, md);
     for (int kt = 0; kt < nk; kt += kPF) {
-        stage_body(kt, xa);
-        if (kt + 1 < nk) stage_body(kt + 1, xb);
-        if (kt + 2 < nk) stage_body(kt + 2, xc);
-        if (kt + 3 < nk) stage_body(kt + 3, xd);
+        stage_body(kt, xa, ma, bA, bB);
+        if (kt + 1 < nk) stage_body(kt + 1, xb, mb, bB, bA);
+        if (kt + 2 < nk) stage_body(kt + 2, xc, mc, bA, bB);
+        if (kt + 3 < nk) stage_body(kt + 3, xd, md, bB, bA);
     }
     mbar_wait(&mbar[2], 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
