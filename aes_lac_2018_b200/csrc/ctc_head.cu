@@ -419,6 +419,14 @@ namespace {
 
 size_t up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
+int sm_count()
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+        sms = 148;
+    return sms;
+}
+
 struct HeadLayout {
     int VP, RB, rows_per_block;
     size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, off_bc, off_wtc, total;
@@ -429,7 +437,7 @@ HeadLayout head_layout(int N, int H, int V)
     HeadLayout l;
     l.VP = (V <= 32) ? 32 : 64;
     const int tiles = (H + 127) / 128;
-    int rb = std::max(1, (4 * 148 + tiles - 1) / tiles);   // two waves of two resident CTAs per SM for the weight-gradient pass
+    int rb = std::max(1, (4 * 148) / tiles);               // at most two waves of two resident CTAs per SM for the weight-gradient pass
     int rows = (N + rb - 1) / rb;
     rows = std::max(32, (rows + 31) / 32 * 32);
     l.rows_per_block = rows;
@@ -508,9 +516,14 @@ ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *c)
     cudaStream_t s = (cudaStream_t)c->stream;
     if (c->training) {
         if (!ok(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * H, s), "memset", st)) return st;
-        const int ctas = std::min((N + 31) / 32, 148 * 8);     // two full waves of 4 resident CTAs per SM
+        // one balanced wave: as many CTAs as are resident at once (round 1 launched 1.6 waves of equal CTAs), and a
+        // block of just enough warps for the H / 4 float4 columns (H = 800: 224 threads, 200 of them busy, instead of 256)
+        const int threads = std::min(256, ((H >> 2) + 31) / 32 * 32);
+        int per_sm = 4;
+        if (!ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, head_stats_kernel, threads, 0), "occupancy", st)) return st;
+        const int ctas = std::max(1, std::min((N + 31) / 32, sm_count() * std::max(1, per_sm)));
         const int rows = (N + ctas - 1) / ctas;
-        head_stats_kernel<<<(N + rows - 1) / rows, 256, 0, s>>>(c->x, N, H, rows, sums);
+        head_stats_kernel<<<(N + rows - 1) / rows, threads, 0, s>>>(c->x, N, H, rows, sums);
         ctcb200_count_launch();
     }
     head_fold_kernel<<<dim3((H + 127) / 128, l.VP / 8), 128, 0, s>>>(c->x, sums, N, H, V, l.VP, c->bn_weight, c->bn_bias, c->running_mean,
@@ -522,12 +535,13 @@ ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *c)
         const int nk = (H + tc::kBK - 1) / tc::kBK;
         tc::head_fold_tc_kernel<<<(nk * 8 * l.VP + 127) / 128, 128, 0, s>>>(wk, H, l.VP, bc);
         const int smem = tc::head_tc_smem_bytes(l.VP);
+        const int grid = (N + tc::kBM - 1) / tc::kBM;
         if (l.VP == 32) {
             if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
-            tc::head_fwd_tc_kernel<32><<<(N + 127) / 128, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
+            tc::head_fwd_tc_kernel<32><<<grid, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
         } else {
             if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
-            tc::head_fwd_tc_kernel<64><<<(N + 127) / 128, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
+            tc::head_fwd_tc_kernel<64><<<grid, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
         }
     }
     for (int i = 0; i < 4; ++i) ctcb200_count_launch();    // fold, bias, fold_tc, forward

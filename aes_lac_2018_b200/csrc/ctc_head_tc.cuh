@@ -69,6 +69,14 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -211,6 +219,13 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
         if (kt + kPF < nk) gload(kt + kPF, xr, mu);        // (this buffer is free again)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> visible to the MMA
         __syncthreads();
+        // Tried on the box and dropped (T = 750, B = 256, H = 800, V = 29; this version: 176 us):
+        //  * no block barrier -- each warp counts itself in with an atomic and the eighth to arrive issues the MMAs, so that
+        //    no warp waits for the slowest: 211 us (weight gradient 156 -> 193 us);
+        //  * row blocks sized for whole waves (109 instead of 128 rows, 5.95 instead of 5.07 waves): 181 us;
+        //  * 256-byte L2 fills on the x loads (DRAM locality of the 128-byte row pieces): 175 us;
+        //  * persistent CTAs (two per SM) walking the row blocks with the prefetch running across block boundaries, two
+        //    TMEM accumulators and the epilogue of a block deferred into the next block's second stage: 216 us.
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi), bl = smem_u32(Blo);

@@ -94,6 +94,46 @@ def test_gpu_head_forward_backward_vs_restatement(T, B, H, V, shift, training):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("T,B,H,V,training", [(749, 63, 800, 29, True), (300, 61, 672, 43, True), (749, 63, 800, 29, False),
+                                              (1500, 40, 1000, 64, True)])
+def test_gpu_head_long_pipelines_vs_torch_float64_on_the_device(T, B, H, V, training):
+    """Sizes at which every CTA of the tensor-core kernels runs MANY pipeline stages (mbarrier phases wrap, both shared-memory
+    stages and both accumulator buffers are reused, row blocks end inside a tile): the small parity shapes above give each
+    CTA one stage.  Reference: torch's own BatchNorm1d + Linear in float64 on the same device."""
+    from aes_lac_2018_b200.head import _HeadFn
+    N = T * B
+    gen = torch.Generator(device="cuda").manual_seed(T * 7 + V)
+    x = (torch.randn(N, H, device="cuda", generator=gen) * (0.5 + 2.5 * torch.rand(H, device="cuda", generator=gen))
+         + torch.randn(H, device="cuda", generator=gen) + 2.0)
+    dl = torch.randn(N, V, device="cuda", generator=gen)
+    bn = torch.nn.BatchNorm1d(H).cuda().double()
+    lin = torch.nn.Linear(H, V, bias=False).cuda().double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.1)
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    rm, rv = bn.running_mean.float().clone(), bn.running_var.float().clone()
+    bn.train(training)
+    xd = x.double().requires_grad_(True)
+    want = lin(bn(xd))
+    want.backward(dl.double())
+    xt = x.view(T, B, H).clone().requires_grad_(True)
+    Wt = lin.weight.detach().float().requires_grad_(True)
+    gt = bn.weight.detach().float().requires_grad_(True)
+    bt = bn.bias.detach().float().requires_grad_(True)
+    out = _HeadFn.apply(xt, Wt, gt, bt, rm, rv, training, 1e-5, 0.1, False)
+    out.backward(dl.view(T, B, V))
+
+    def rel(got, ref):
+        return float((got.double().reshape(ref.shape) - ref).abs().max() / ref.abs().max())
+    assert rel(out.detach(), want.detach()) < 2e-5
+    assert rel(xt.grad, xd.grad) < 1e-4
+    assert rel(Wt.grad, lin.weight.grad) < 1e-4
+    assert rel(gt.grad, bn.weight.grad) < 1e-4 and rel(bt.grad, bn.bias.grad) < 1e-4
+    if training:
+        assert rel(rm, bn.running_mean) < 1e-5 and rel(rv, bn.running_var) < 1e-5
+
+
+@pytest.mark.gpu
 def test_module_is_a_drop_in_for_the_reference_head_and_feeds_the_ctc_engine():
     """Same parameters loaded into torch's own BatchNorm1d + Linear (the reference's head, float64 on the CPU) and into
     the fused module; then head -> CTCLoss -> backward end to end against restatement(head) + oracle(CTC)."""
