@@ -9,8 +9,8 @@
 // PyTorch runs this as 3 kernels over x-sized tensors forward and 5 backward.  Here, with V <= 64 the op is a
 // *skinny* product -- 2*V flops per 4 bytes of x, far below the tensor-core ridge and close to the fp32 FMA
 // ridge -- so it is organised around reading x as few times as possible.  The forward product runs on the tensor
-// cores with an error-compensated tf32 split, the backward products in fp32 FMAs (the reference computes in fp32; no
-// plain tf32/bf16 rounding is introduced anywhere):
+// cores with an error-compensated tf32 split, and since round 2 so do both backward products (the reference computes in
+// fp32; no plain tf32/bf16 rounding is introduced anywhere):
 //
 //   forward   head_stats_kernel   one pass over x: per-feature sum / sum of squares (shifted by row 0, fp64 merge)
 //             head_fold_kernel    BatchNorm's scale folded into the weights: Wk[h][v] = W[v][h] * gamma_h * invstd_h;
@@ -23,12 +23,14 @@
 //                                 |mu| >> sigma the folded form cancels catastrophically in fp32.  Rows are written in
 //                                 T x B x V order -- exactly what ctc_fused_kernel reads
 //   backward  head_colsum_kernel  s[v] = sum_n dlogits[n][v]
-//             head_wgrad_kernel   one pass over x: G[v][h] = sum_n dlogits[n][v] * (x[n][h] - mu_h)  (per-row-block
-//                                 partials, reduced in a fixed order => deterministic)
+//             head_wgrad_tc_kernel (ctc_head_bwd_tc.cuh)  one pass over x on the tensor cores:
+//                                 G[v][h] = sum_n dlogits[n][v] * (x[n][h] - mu_h)  (per-row-block partials, reduced in a
+//                                 fixed order => deterministic)
 //             head_reduce_kernel, head_finalize_kernel  from G and s alone: dW, dgamma, dbeta and the per-feature coefficients
 //                                 of dx = A_h * (dlogits W)[n][h] + B_h + C_h * (x[n][h] - mu_h)   (BatchNorm's backward
 //                                 needs only column reductions that are linear in G and s)
-//             head_dgrad_kernel   one pass over x: dx as above
+//             head_wt_tc_kernel, head_dgrad_tc_kernel (ctc_head_bwd_tc.cuh)  one pass over x, dx as above, the product
+//                                 dlogits W on the tensor cores
 // => x is read 2x forward and 2x backward and dx written once; nothing else of size N x H exists.
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -44,12 +46,6 @@
 
 namespace ctcb200 {
 
-__device__ __forceinline__ void hd_cp_async16(void *smem_dst, const void *gsrc)
-{
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void hd_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 // 16-byte read-only load that ptxas may not sink next to its first use: a batch of these is issued back to back, so a
 // thread really has the whole batch in flight (with plain __ldg the compiler re-used one register and serialised them)
 __device__ __forceinline__ float4 hd_ldg_f4(const float *p)
@@ -58,9 +54,6 @@ __device__ __forceinline__ float4 hd_ldg_f4(const float *p)
     asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-template <int N>
-__device__ __forceinline__ void hd_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
-
 // ---------------------------------------------------------------------------------------------------------
 // batch statistics: sums[0][h] = sum_n (x[n][h] - x[0][h]),  sums[1][h] = sum_n (x[n][h] - x[0][h])^2
 // (shifting by the first row removes the cancellation of E[x^2] - E[x]^2 for features with a large mean)
@@ -183,93 +176,6 @@ __global__ void __launch_bounds__(256) head_colsum_kernel(const float *__restric
     }
 }
 
-// part[rb][v][h] = sum over the rows of block rb of dl[n][v] * x[n][h]
-template <int VP>
-__global__ void __launch_bounds__(128) head_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ dl,
-                                                         const float *__restrict__ mean, float *__restrict__ part, int N,
-                                                         int H, int V, int rows_per_block)
-{
-    constexpr int BR = 16, BH = 128, TV = VP / 8;
-    __shared__ __align__(16) float xs[2][BR][BH];
-    __shared__ __align__(16) float ds[2][BR][VP];
-    const int tid = threadIdx.x, tv = tid >> 4, th = tid & 15;     // classes tv*TV.., features th*4.. and 64 + th*4..
-    const int h0 = blockIdx.x * BH;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(N, r0 + rows_per_block);
-    float acc[TV][8];
-#pragma unroll
-    for (int i = 0; i < TV; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    const int nt = (r1 - r0 + BR - 1) / BR;
-
-    auto load_tile = [&](int t, int buf) {
-        const int rb = r0 + t * BR;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                      // 16 rows x 32 float4
-            const int idx = tid + i * 128, r = idx >> 5, c4 = idx & 31;
-            const int n = rb + r, h = h0 + c4 * 4;
-            float *dst = &xs[buf][r][c4 * 4];
-            if (n < r1 && h < H) hd_cp_async16(dst, x + (size_t)n * H + h);
-            else *(float4 *)dst = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        hd_commit();
-        for (int idx = tid; idx < BR * VP; idx += 128) {   // rows of V floats are not 16-byte aligned: plain loads
-            const int r = idx / VP, v = idx % VP;
-            const int n = rb + r;
-            ds[buf][r][v] = (n < r1 && v < V) ? __ldg(dl + (size_t)n * V + v) : 0.f;
-        }
-    };
-
-    if (nt > 0) load_tile(0, 0);
-    for (int t = 0; t < nt; ++t) {
-        const int buf = t & 1;
-        if (t + 1 < nt) { load_tile(t + 1, buf ^ 1); hd_wait<1>(); }
-        else hd_wait<0>();
-        {   // centre the tile: every thread fixes up the float4 it copied itself (its own cp.async have landed);
-            // padding rows meet dl = 0
-            const int c4 = tid & 31, h = h0 + c4 * 4;
-            if (h < H) {
-                const float4 mu = __ldg((const float4 *)(mean + h));
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 *p = (float4 *)&xs[buf][(tid + i * 128) >> 5][c4 * 4];
-                    float4 v = *p;
-                    v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
-                    *p = v;
-                }
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < BR; ++r) {
-            const float4 xa = *(const float4 *)&xs[buf][r][th * 4];
-            const float4 xb = *(const float4 *)&xs[buf][r][64 + th * 4];
-            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            float dv[TV];
-#pragma unroll
-            for (int i4 = 0; i4 < TV; i4 += 4) {
-                const float4 d4 = *(const float4 *)&ds[buf][r][tv * TV + i4];
-                dv[i4] = d4.x; dv[i4 + 1] = d4.y; dv[i4 + 2] = d4.z; dv[i4 + 3] = d4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < TV; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], xv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-    float *pp = part + (size_t)blockIdx.y * VP * H;
-#pragma unroll
-    for (int i = 0; i < TV; ++i) {
-        const int v = tv * TV + i;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int h = h0 + ((j < 4) ? th * 4 + j : 64 + th * 4 + (j - 4));
-            if (h < H) pp[(size_t)v * H + h] = acc[i][j];
-        }
-    }
-}
-
 // reduce the row-block partials in a fixed order (deterministic): one thread per (class, feature).
 // Leaves gx[v][h] = sum_n dlogits[n][v] * xhat[n][h] in the first slab of `part` and writes dW.
 __global__ void __launch_bounds__(128) head_reduce_kernel(float *__restrict__ part, int RB, int VP, const double *__restrict__ s,
@@ -316,104 +222,6 @@ __global__ void head_finalize_kernel(const float *__restrict__ gxs, const double
     coef[h] = (float)A; coef[H + h] = (float)B; coef[2 * H + h] = (float)C; coef[3 * H + h] = (float)mu;
 }
 
-// dx[n][h] = A_h * sum_v dl[n][v] W[v][h] + B_h + C_h (x[n][h] - mu_h)
-// One CTA owns a 128-feature slice of W (kept in shared memory) and walks `blocks_per_cta` consecutive 64-row blocks;
-// the dlogits tile and the x values of the NEXT block are requested before / right after the products of the current one.
-template <int VP>
-__global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict__ x, const float *__restrict__ dl,
-                                                         const float *__restrict__ W, const float *__restrict__ coef,
-                                                         float *__restrict__ dx, int N, int H, int V, int blocks_per_cta)
-{
-    constexpr int BM = 64, BH = 128, DQ = BM * VP / 256;          // dlogits values per thread and block
-    __shared__ __align__(16) float wt[VP][BH];
-    __shared__ __align__(16) float dls[VP][BM];           // row r of the block sits at column (r % 16) * 4 + r / 16: the four
-                                                           // rows tr, tr+16, tr+32, tr+48 of a thread are one float4
-    const int tid = threadIdx.x, tr = tid >> 4, th = tid & 15;     // rows tr + 16 i; features th*4.. and 64 + th*4..
-    const int h0 = blockIdx.x * BH;
-    const int nblk = (N + BM - 1) / BM;
-    const int b0 = blockIdx.y * blocks_per_cta, b1 = min(nblk, b0 + blocks_per_cta);
-    if (b0 >= b1) return;
-
-    auto load_x = [&](int blk, float4 (&xq)[2][4]) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = min(h0 + half * 64 + th * 4, H - 4), n = min(blk * BM + tr + 16 * i, N - 1);
-                xq[half][i] = hd_ldg_f4(x + (size_t)n * H + h);
-            }
-    };
-    auto load_dl = [&](int blk, float (&dq)[DQ]) {
-#pragma unroll
-        for (int q = 0; q < DQ; ++q) {
-            const int idx = tid + q * 256, r = idx / VP, v = idx % VP;
-            const int n = blk * BM + r;
-            dq[q] = (n < N && v < V) ? __ldg(dl + (size_t)n * V + v) : 0.f;
-        }
-    };
-    float4 xq[2][4];
-    float dq[DQ];
-    load_x(b0, xq);
-    load_dl(b0, dq);
-    for (int idx = tid; idx < VP * BH / 4; idx += 256) {
-        const int v = idx / (BH / 4), c4 = idx % (BH / 4);
-        const int h = h0 + c4 * 4;
-        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v < V && h < H) w4 = __ldg((const float4 *)(W + (size_t)v * H + h));
-        *(float4 *)&wt[v][c4 * 4] = w4;
-    }
-    for (int blk = b0; blk < b1; ++blk) {
-        const int n0 = blk * BM;
-        __syncthreads();                                   // the previous block's readers of dls are done
-#pragma unroll
-        for (int q = 0; q < DQ; ++q) {
-            const int idx = tid + q * 256, r = idx / VP;
-            dls[idx % VP][(r & 15) * 4 + (r >> 4)] = dq[q];
-        }
-        __syncthreads();
-        if (blk + 1 < b1) load_dl(blk + 1, dq);            // (dq is free again; lands while the products are formed)
-        float acc[4][8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-        for (int v = 0; v < V; ++v) {
-            const float4 wa = *(const float4 *)&wt[v][th * 4];
-            const float4 wb = *(const float4 *)&wt[v][64 + th * 4];
-            const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-            const float4 d4 = *(const float4 *)&dls[v][tr * 4];
-            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(dv[i], wv[j], acc[i][j]);
-            }
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int h = h0 + half * 64 + th * 4;
-            if (h >= H) continue;
-            const float4 A = __ldg((const float4 *)(coef + h));
-            const float4 B = __ldg((const float4 *)(coef + H + h));
-            const float4 C = __ldg((const float4 *)(coef + 2 * H + h));
-            const float4 M = __ldg((const float4 *)(coef + 3 * H + h));
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int n = n0 + tr + 16 * i;
-                if (n >= N) continue;
-                const float4 xv = xq[half][i];
-                float4 o;
-                o.x = fmaf(A.x, acc[i][half * 4 + 0], fmaf(C.x, xv.x - M.x, B.x));
-                o.y = fmaf(A.y, acc[i][half * 4 + 1], fmaf(C.y, xv.y - M.y, B.y));
-                o.z = fmaf(A.z, acc[i][half * 4 + 2], fmaf(C.z, xv.z - M.z, B.z));
-                o.w = fmaf(A.w, acc[i][half * 4 + 3], fmaf(C.w, xv.w - M.w, B.w));
-                *(float4 *)(dx + (size_t)n * H + h) = o;
-            }
-        }
-        if (blk + 1 < b1) load_x(blk + 1, xq);             // used after the next block's products
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
@@ -428,14 +236,15 @@ int sm_count()
 }
 
 struct HeadLayout {
-    int VP, RB, rows_per_block;
+    int VP, VPW, RB, rows_per_block;   // classes padded for the forward / input-gradient MMAs (32, 48, 64) and for the weight gradient (32, 64)
     size_t off_sums, off_wk, off_shift, off_bias, off_s, off_coef, off_mean, off_invstd, off_part, off_bc, off_wtc, total;
 };
 
 HeadLayout head_layout(int N, int H, int V)
 {
     HeadLayout l;
-    l.VP = (V <= 32) ? 32 : 64;
+    l.VP = (V <= 32) ? 32 : (V <= 48) ? 48 : 64;
+    l.VPW = (V <= 32) ? 32 : 64;
     const int tiles = (H + 127) / 128;
     int rb = std::max(1, (4 * 148) / tiles);               // at most two waves of two resident CTAs per SM for the weight-gradient pass
     int rows = (N + rb - 1) / rb;
@@ -451,7 +260,7 @@ HeadLayout head_layout(int N, int H, int V)
     l.off_coef = o;   o += up(sizeof(float) * 4 * H);
     l.off_mean = o;   o += up(sizeof(float) * H);
     l.off_invstd = o; o += up(sizeof(float) * H);
-    l.off_part = o;   o += up(sizeof(float) * (size_t)l.RB * l.VP * H);
+    l.off_part = o;   o += up(sizeof(float) * (size_t)l.RB * l.VPW * H);
     l.off_bc = o;     o += up(tc::head_tc_weight_bytes(H, l.VP));
     l.off_wtc = o;    o += up(tc::head_dgrad_tc_weight_bytes(H, l.VP));
     l.total = o;
@@ -536,13 +345,11 @@ ctcStatus_t ctc_b200_head_forward(const ctcB200HeadForward *c)
         tc::head_fold_tc_kernel<<<(nk * 8 * l.VP + 127) / 128, 128, 0, s>>>(wk, H, l.VP, bc);
         const int smem = tc::head_tc_smem_bytes(l.VP);
         const int grid = (N + tc::kBM - 1) / tc::kBM;
-        if (l.VP == 32) {
-            if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
-            tc::head_fwd_tc_kernel<32><<<grid, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
-        } else {
-            if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
-            tc::head_fwd_tc_kernel<64><<<grid, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax);
-        }
+#define FWD_LAUNCH(VPX) do { \
+            if (!ok(cudaFuncSetAttribute(tc::head_fwd_tc_kernel<VPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st; \
+            tc::head_fwd_tc_kernel<VPX><<<grid, tc::kThreads, smem, s>>>(c->x, bc, bias, mean, c->out, N, H, V, c->softmax); } while (0)
+        if (l.VP == 32) FWD_LAUNCH(32); else if (l.VP == 48) FWD_LAUNCH(48); else FWD_LAUNCH(64);
+#undef FWD_LAUNCH
     }
     for (int i = 0; i < 4; ++i) ctcb200_count_launch();    // fold, bias, fold_tc, forward
     if (!ok(cudaGetLastError(), "head forward launch", st)) return st;
@@ -569,15 +376,10 @@ ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *c)
         const int rows = (N + ctas - 1) / ctas;
         head_colsum_kernel<<<(N + rows - 1) / rows, 256, 0, s>>>(c->dlogits, N, V, rows, sv);
     }
-    // CTC_B200_HEAD_FMA=1: the round-1 fp32-FMA backward kernels (A/B timing and debugging only)
-    static const bool fma_path = std::getenv("CTC_B200_HEAD_FMA") != nullptr;
     const dim3 gw((H + 127) / 128, l.RB);
-    if (fma_path) {
-        if (l.VP == 32) head_wgrad_kernel<32><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
-        else head_wgrad_kernel<64><<<gw, 128, 0, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
-    } else {
-        const int smem = tc::head_wgrad_tc_smem_bytes(l.VP);
-        if (l.VP == 32) {
+    {
+        const int smem = tc::head_wgrad_tc_smem_bytes(l.VPW);
+        if (l.VPW == 32) {
             if (!ok(cudaFuncSetAttribute(tc::head_wgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
             tc::head_wgrad_tc_kernel<32><<<gw, 256, smem, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
         } else {
@@ -585,36 +387,26 @@ ctcStatus_t ctc_b200_head_backward(const ctcB200HeadBackward *c)
             tc::head_wgrad_tc_kernel<64><<<gw, 256, smem, s>>>(c->x, c->dlogits, c->save_mean, part, N, H, V, l.rows_per_block);
         }
     }
-    head_reduce_kernel<<<dim3((H + 127) / 128, V), 128, 0, s>>>(part, l.RB, l.VP, sv, H, c->bn_weight, c->bn_bias,
+    head_reduce_kernel<<<dim3((H + 127) / 128, V), 128, 0, s>>>(part, l.RB, l.VPW, sv, H, c->bn_weight, c->bn_bias,
                                                                 c->save_invstd, c->dweight);
     head_finalize_kernel<<<(H + 127) / 128, 128, 0, s>>>(part, sv, N, H, V, c->weight, c->bn_weight, c->save_mean,
                                                         c->save_invstd, c->training, c->dbn_weight, c->dbn_bias, coef);
     ctcb200_count_launch();
     ctcb200_count_launch(); ctcb200_count_launch(); ctcb200_count_launch();
-    if (c->dx && fma_path) {
-        const int tiles = (H + 127) / 128, nblk = (N + 63) / 64;
-        const int groups = std::max(1, std::min(nblk, (148 * 6 + tiles - 1) / tiles));    // ~6 CTAs per SM in flight
-        const int bpc = (nblk + groups - 1) / groups;
-        const dim3 gd(tiles, (nblk + bpc - 1) / bpc);
-        if (l.VP == 32) head_dgrad_kernel<32><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V, bpc);
-        else head_dgrad_kernel<64><<<gd, 256, 0, s>>>(c->x, c->dlogits, c->weight, coef, c->dx, N, H, V, bpc);
-        ctcb200_count_launch();
-    } else if (c->dx) {
+    if (c->dx) {
         float4 *wtc = (float4 *)(ws + l.off_wtc);
         const int tiles = (H + tc::kDBM - 1) / tc::kDBM, nblk = (N + tc::kDBN - 1) / tc::kDBN;
         tc::head_wt_tc_kernel<<<(tiles * (l.VP / 4) * tc::kDBM + 127) / 128, 128, 0, s>>>(c->weight, H, V, l.VP, wtc);
-        const int resident = (l.VP == 32) ? 2 : 1;
-        const int groups = std::max(1, std::min(nblk, (148 * resident * 2 + tiles - 1) / tiles));   // two waves of resident CTAs
+        const int resident = (l.VP <= 48) ? 2 : 1;
+        const int groups = std::max(1, std::min(nblk, (sm_count() * resident * 2 + tiles - 1) / tiles));   // two waves of resident CTAs
         const int bpc = (nblk + groups - 1) / groups;
         const dim3 gd(tiles, (nblk + bpc - 1) / bpc);
         const int smem = tc::head_dgrad_tc_smem_bytes(l.VP);
-        if (l.VP == 32) {
-            if (!ok(cudaFuncSetAttribute(tc::head_dgrad_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
-            tc::head_dgrad_tc_kernel<32><<<gd, 256, smem, s>>>(c->x, c->dlogits, wtc, coef, c->dx, N, H, V, bpc);
-        } else {
-            if (!ok(cudaFuncSetAttribute(tc::head_dgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st;
-            tc::head_dgrad_tc_kernel<64><<<gd, 256, smem, s>>>(c->x, c->dlogits, wtc, coef, c->dx, N, H, V, bpc);
-        }
+#define DG_LAUNCH(VPX) do { \
+            if (!ok(cudaFuncSetAttribute(tc::head_dgrad_tc_kernel<VPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "smem attribute", st)) return st; \
+            tc::head_dgrad_tc_kernel<VPX><<<gd, 256, smem, s>>>(c->x, c->dlogits, wtc, coef, c->dx, N, H, V, bpc); } while (0)
+        if (l.VP == 32) DG_LAUNCH(32); else if (l.VP == 48) DG_LAUNCH(48); else DG_LAUNCH(64);
+#undef DG_LAUNCH
         ctcb200_count_launch(); ctcb200_count_launch();
     }
     if (!ok(cudaGetLastError(), "head backward launch", st)) return st;

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_tc_kernel(const float *__re
 // ---------------------------------------------------------------------------------------------------------
 // input gradient
 constexpr int kDBM = 128, kDBN = 128;                      // features per CTA (TMEM lanes), rows per block (TMEM columns)
-__host__ __device__ inline int head_dgrad_tc_smem_bytes(int VP) { return 6 * kDBM * VP * 4; }
+__host__ __device__ inline int head_dgrad_tc_smem_bytes(int VP) { return 4 * kDBM * VP * 4; }
 __host__ __device__ inline size_t head_dgrad_tc_weight_bytes(int H, int VP) { return (size_t)((H + kDBM - 1) / kDBM) * 2 * kDBM * VP * 4; }
 
 // W[v][h] split into tf32 hi / lo and laid out as the K-major canonical A tiles of the input-gradient MMA:
@@ -230,7 +230,7 @@ __global__ void head_wt_tc_kernel(const float *__restrict__ W, int H, int V, int
 }
 
 template <int VP>
-__global__ void __launch_bounds__(256, (VP == 32) ? 2 : 1)
+__global__ void __launch_bounds__(256, (VP <= 48) ? 2 : 1)
 head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, const float4 *__restrict__ wtc,
                      const float *__restrict__ coef, float *__restrict__ dx, int N, int H, int V, int blocks_per_cta)
 {
@@ -240,7 +240,8 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t tmem_base_s;
     float4 *const Whi = (float4 *)hsm, *const Wlo = Whi + T_F4;
-    float *const dbuf = (float *)(Wlo + T_F4);             // [buffer][hi | lo][VP/4 columns][128 rows][4]
+    float *const dbuf = (float *)(Wlo + T_F4);             // [hi | lo][VP/4 columns][128 rows][4]; ONE buffer: a block's MMAs are
+                                                           // waited for before its epilogue anyway, the next tile is staged right after
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int h0 = blockIdx.x * kDBM;
     const int nblk = (N + kDBN - 1) / kDBN;
@@ -261,7 +262,7 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
         const float4 *src = wtc + (size_t)blockIdx.x * 2 * T_F4;
         for (int i = tid; i < 2 * T_F4; i += 256) Whi[i] = __ldg(src + i);
         float4 *d4 = (float4 *)dbuf;
-        for (int i = tid; i < 4 * T_F4; i += 256) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < 2 * T_F4; i += 256) d4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -299,8 +300,8 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
             dq[q] = (idx < lim) ? __ldg(d + idx) : 0.f;
         }
     };
-    auto stage_dl = [&](int buf, const float (&dq)[DQ]) {
-        float *const hi = dbuf + (size_t)buf * 2 * kDBN * VP, *const lo = hi + kDBN * VP;
+    auto stage_dl = [&](const float (&dq)[DQ]) {
+        float *const hi = dbuf, *const lo = hi + kDBN * VP;
 #pragma unroll
         for (int q = 0; q < DQ; ++q) {
             uint32_t pk;                                   // (opaque: keeps the unpacked offsets out of the loop-invariant set)
@@ -319,7 +320,7 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
         int buf;                                           // opaque to the optimiser: otherwise the 48 descriptors of the two
         asm volatile("and.b32 %0, %1, 1;" : "=r"(buf) : "r"(li));   // buffers are hoisted out of the block loop as ~100 live registers
         const uint32_t wh = smem_u32(Whi), wl = smem_u32(Wlo);
-        const uint32_t dh = smem_u32(dbuf + (size_t)buf * 2 * kDBN * VP), dlo = dh + kDBN * VP * 4;
+        const uint32_t dh = smem_u32(dbuf), dlo = dh + kDBN * VP * 4;
         const uint32_t acc = tmem + buf * kDBN;
 #pragma unroll
         for (int j = 0; j < VP / 8; ++j) {                 // K = 8 classes = two 16-byte columns of 128 rows
@@ -335,7 +336,7 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
 
     float dq[DQ];
     load_dl(b0, dq);
-    stage_dl(0, dq);
+    stage_dl(dq);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -366,16 +367,13 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
             }
         };
         load_x(0);
-        if (li + 1 < nb) stage_dl((li + 1) & 1, dq);       // (its last reader, the MMAs of block li-1, completed before epilogue li-1)
+        mbar_wait(&mbar[li & 1], (uint32_t)((li >> 1) & 1));       // this block's MMAs are complete: the dl buffer is free
+        if (li + 1 < nb) stage_dl(dq);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
-        if (tid == 0 && li + 1 < nb) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_mma(li + 1);
-        }
-        mbar_wait(&mbar[li & 1], (uint32_t)((li >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0 && li + 1 < nb) issue_mma(li + 1);    // (runs beside this block's epilogue, into the other accumulator)
         load_x(1);                                         // in flight while the first half is combined and stored
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                      // 16 rows at a time (32 made ptxas spill under the 128-register cap)

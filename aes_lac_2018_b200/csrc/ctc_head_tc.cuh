@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
 {
     constexpr int A_F4 = kBM * kBK / 4;                    // float4 per A tile (one of hi / lo)
     constexpr int B_F4 = VP * kBK / 4;
+    constexpr int TCOLS = VP <= 32 ? 32 : 64;              // TMEM columns are allocated in powers of two (VP = 32, 48, 64)
     extern __shared__ __align__(1024) unsigned char hsm_raw[];
     __shared__ __align__(8) uint64_t mbar[3];              // [0], [1]: stage free again; [2]: accumulator complete
     __shared__ uint32_t tmem_base_s;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
     }
     if (warp == 0) {
         __syncwarp();                                      // (.sync.aligned below: the warp must be converged after the tid == 0 block)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(VP) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -264,12 +265,12 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
     if (warp < 4) {
     float val[VP];
 #pragma unroll
-    for (int h = 0; h < VP / 32; ++h) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + h * 32, v);
+    for (int h = 0; h < VP / 16; ++h) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + h * 16, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) val[h * 32 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) val[h * 16 + j] = __uint_as_float(v[j]);
     }
 #pragma unroll
     for (int j = 0; j < VP; ++j) val[j] += __ldg(bias + j);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(VP) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
 }
 
 }  // namespace tc
