@@ -375,7 +375,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
         // "previous label" vector of pair m is then pair m - 1 itself (no repacking), only pair 0 takes the neighbour
         // lane's value.  Same operations in the same order per element as the scalar form: bit-identical results.
         constexpr int H2 = NL / 2;
-        constexpr bool PK = ((CTC_W32_PACKED_MASK >> NL) & 1) != 0;   // packed recursion for this variant (measured per NS)
+        constexpr bool PK = VCH == 1 && ((CTC_W32_PACKED_MASK >> NL) & 1) != 0;   // packed recursion for this variant (measured per NS, one-slice alphabets)
         f32x2 mskp[H2 > 0 ? H2 : 1], msk1p[H2 > 0 ? H2 : 1];   // (msk[m], msk[m+H2]) and the same one label up (beta)
 #pragma unroll
         for (int m = 0; m < H2; ++m) { mskp[m] = pk2(msk[m], msk[m + H2]); msk1p[m] = pk2(msk[m + 1], msk[m + H2 + 1]); }
