@@ -97,6 +97,11 @@ typedef unsigned long long f32x2;
 #ifndef CTC_W32_PACKED_MASK
 #define CTC_W32_PACKED_MASK 0x00d0      /* NS = 8, 12, 14 */
 #endif
+// the same for two-slice alphabets (V = 32 .. 63; V = 43, their own register caps): NS = 4: 4.52 -> 4.56, 6: 3.78 -> 3.81,
+// 8: 3.08 -> 2.96, 10: 2.62 -> 2.74, 12: 2.30 -> 2.26, 14: 1.98 -> 1.66, 16: 1.64 -> 1.73
+#ifndef CTC_W32_PACKED_MASK2
+#define CTC_W32_PACKED_MASK2 0x0120     /* NS = 10, 16 */
+#endif
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ float lo2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
 __device__ __forceinline__ float hi2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
@@ -375,7 +380,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
         // "previous label" vector of pair m is then pair m - 1 itself (no repacking), only pair 0 takes the neighbour
         // lane's value.  Same operations in the same order per element as the scalar form: bit-identical results.
         constexpr int H2 = NL / 2;
-        constexpr bool PK = VCH == 1 && ((CTC_W32_PACKED_MASK >> NL) & 1) != 0;   // packed recursion for this variant (measured per NS, one-slice alphabets)
+        constexpr bool PK = (((VCH == 1 ? CTC_W32_PACKED_MASK : CTC_W32_PACKED_MASK2) >> NL) & 1) != 0;   // packed recursion for this variant (measured per NS, one-slice alphabets)
         f32x2 mskp[H2 > 0 ? H2 : 1], msk1p[H2 > 0 ? H2 : 1];   // (msk[m], msk[m+H2]) and the same one label up (beta)
 #pragma unroll
         for (int m = 0; m < H2; ++m) { mskp[m] = pk2(msk[m], msk[m + H2]); msk1p[m] = pk2(msk[m + 1], msk[m + H2 + 1]); }

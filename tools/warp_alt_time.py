@@ -24,7 +24,7 @@ out = []
 for spec in sys.argv[1].split(","):
     lo, hi = (spec.split("-") + [spec])[:2] if "-" in spec else (spec, spec)
     try:
-        ms, loss, st = run(8192, int(lo), int(hi), os.environ.get("ALT_MODE", "warp"))
+        ms, loss, st = run(8192, int(lo), int(hi), os.environ.get("ALT_MODE", "warp"), V=int(os.environ.get("ALT_V", "29")))
         out.append("L%%s: %%.3f ms %%.2f M/s st%%d" %% (spec, ms, 8192 / ms / 1e3, st))
     except Exception as e:
         out.append("L%%s: ERR %%s" %% (spec, str(e)[:60]))
