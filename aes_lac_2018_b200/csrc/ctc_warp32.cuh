@@ -622,15 +622,17 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             if constexpr (PK) {
 #pragma unroll
             for (int tt = KK - 1; tt >= 0; --tt) {
-                const float dn0 = __shfl_down_sync(kFull, bt[0], 1) * fd, dn1 = __shfl_down_sync(kFull, bt[1], 1) * fd;
+                // what the lane below needs from this one is only  blank 0 + (skip allowed) * label 0  of its last label's
+                // successor sum: one shuffle instead of two (msk[0] here is the msk[NL] of the lane below)
+                const float dnc = __shfl_down_sync(kFull, fmaf(msk[0], bt[1], bt[0]), 1) * fd;
                 float *prow = prod + tt * PS;
                 float pl[NL];
 #pragma unroll
                 for (int jj = 0; jj < NL; ++jj) pl[jj] = lookup(rcur[tt], lsrc[jj]);
                 const f32x2 pbb = pk2(pbv[tt], pbv[tt]);
                 f32x2 nL[H2 > 0 ? H2 : 1], nB[H2 > 0 ? H2 : 1];
-                auto Bk = [&](int j) -> float { return (j < NL) ? bt[2 * (j < NL ? j : 0)] : dn0; };        // blank j (NL: lane above)
-                auto Lb = [&](int j) -> float { return (j < NL) ? bt[2 * (j < NL ? j : 0) + 1] : dn1; };    // label j
+                auto Bk = [&](int j) -> float { return (j < NL) ? bt[2 * (j < NL ? j : 0)] : dnc; };        // blank j (NL: from the lane above, combined)
+                auto Lb = [&](int j) -> float { return (j < NL) ? bt[2 * (j < NL ? j : 0) + 1] : 0.f; };    // label j
 #pragma unroll
                 for (int m = 0; m < H2; ++m) {
                     const f32x2 PL = pk2(Lb(m), Lb(m + H2)), PB = pk2(Bk(m), Bk(m + H2));
@@ -649,7 +651,7 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
                 float oL = 0.f, oB = 0.f;
                 if (NL & 1) {
                     constexpr int j = NL - 1;
-                    const float tb = fmaf(msk[j + 1], dn1, bt[2 * j + 1] + dn0);
+                    const float tb = bt[2 * j + 1] + dnc;
                     const float pr = av[tt][j] * tb;
                     const float tbb = bt[2 * j] + bt[2 * j + 1];
                     if (tt == 0) { qf += pr; qf = fmaf(ab0[j], tbb, qf); }
@@ -668,16 +670,14 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             } else {
 #pragma unroll
             for (int tt = KK - 1; tt >= 0; --tt) {
-                const float dn0 = __shfl_down_sync(kFull, bt[0], 1) * fd, dn1 = __shfl_down_sync(kFull, bt[1], 1) * fd;
+                const float dnc = __shfl_down_sync(kFull, fmaf(msk[0], bt[1], bt[0]), 1) * fd;   // (see the packed form)
                 float *prow = prod + tt * PS;
 #pragma unroll
                 for (int i = 0; i < NS; ++i) {
                     if (i & 1) {
                         const int jj = i >> 1;
                         const float pl = lookup(rcur[tt], lsrc[jj]);
-                        const float s1 = bt[i] + ((i + 1 < NS) ? bt[i + 1] : dn0);
-                        const float n2 = (i + 2 < NS) ? bt[i + 2] : dn1;   // (msk[NL] is 0 on lane 31)
-                        const float tb = fmaf(msk[jj + 1], n2, s1);
+                        const float tb = (i + 2 < NS) ? fmaf(msk[jj + 1], bt[i + 2], bt[i] + bt[i + 1]) : bt[i] + dnc;
                         const float pr = av[tt][jj] * tb;
                         if (tt == 0) qf += pr;
                         if (tt == KK - 1 && KK > 1) ql += pr;
