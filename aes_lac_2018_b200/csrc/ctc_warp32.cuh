@@ -724,12 +724,24 @@ __global__ void __maxnreg__(MAXR) ctc_warp32_kernel(const FusedParams P)
             float acc[VCH][KK];
 #pragma unroll
             for (int v = 0; v < VCH; ++v) {
-#pragma unroll
-                for (int tt = 0; tt < KK; ++tt) acc[v][tt] = 0.f;
                 const float *gp = prod + koff[v];
-                for (int qq = 0; qq < kcnt[v]; ++qq) {
+                if constexpr (PK && KK >= 2) {              // frames summed in pairs (FADD2): half the additions of the loop
+                    f32x2 ap[KK / 2];
 #pragma unroll
-                    for (int tt = 0; tt < KK; ++tt) acc[v][tt] += gp[tt * PS + qq];
+                    for (int u = 0; u < KK / 2; ++u) ap[u] = pk2(0.f, 0.f);
+                    for (int qq = 0; qq < kcnt[v]; ++qq) {
+#pragma unroll
+                        for (int u = 0; u < KK / 2; ++u) ap[u] = add2(ap[u], pk2(gp[(2 * u) * PS + qq], gp[(2 * u + 1) * PS + qq]));
+                    }
+#pragma unroll
+                    for (int u = 0; u < KK / 2; ++u) { acc[v][2 * u] = lo2(ap[u]); acc[v][2 * u + 1] = hi2(ap[u]); }
+                } else {
+#pragma unroll
+                    for (int tt = 0; tt < KK; ++tt) acc[v][tt] = 0.f;
+                    for (int qq = 0; qq < kcnt[v]; ++qq) {
+#pragma unroll
+                        for (int tt = 0; tt < KK; ++tt) acc[v][tt] += gp[tt * PS + qq];
+                    }
                 }
             }
             // gradient rows: lane = symbol (coalesced)
