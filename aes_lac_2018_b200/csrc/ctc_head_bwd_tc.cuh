@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_tc_kernel(const float *__re
     }
     if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(VP) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(2 * VP) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     // the dl tiles: zero once (the pad classes v >= V are never written again)
@@ -115,6 +115,11 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_tc_kernel(const float *__re
     // D = f32, A = B = tf32, both MN-major, N >> 3, M >> 4
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(VP >> 3) << 17) |
                                ((uint32_t)(kWBM >> 4) << 24);
+    // the same with N = 2 VP: the hi and lo tiles of dl lie behind one another (the lo tile is simply the next class
+    // blocks), so a_hi x [b_hi | b_lo] is ONE MMA into 2 VP accumulator columns -- two MMAs per K step instead of three,
+    // x_hi read from shared memory once instead of twice; the epilogue adds the two column halves
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)((2 * VP) >> 3) << 17) |
+                                ((uint32_t)(kWBM >> 4) << 24);
 
     auto stage_body = [&](int kt, float4 (&xr)[4], float (&dq)[DQ]) {
         const int s = kt & 1;
@@ -144,16 +149,15 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_tc_kernel(const float *__re
         //  that no warp waits for the slowest.  Slower on the box: weight gradient 156 -> 193 us, forward 179 -> 211 us.)
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi), bl = smem_u32(Blo);
+            const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi);
 #pragma unroll
             for (int j = 0; j < kWBK / 8; ++j) {           // one MMA = 8 rows (K = 8 tf32) = two 512-byte atoms
                 const uint32_t o = j * 1024;
                 // LBO = the next 32 features / classes (4096 B), SBO = the next atom of four rows (512 B)
                 const uint64_t dah = smem_desc_sw(ah + o, 4096, 512, 1), dal = smem_desc_sw(al + o, 4096, 512, 1);
-                const uint64_t dbh = smem_desc_sw(bh + o, 4096, 512, 1), dbl = smem_desc_sw(bl + o, 4096, 512, 1);
-                mma_tf32(tmem, dal, dbh, idesc, (kt > 0 || j > 0) ? 1u : 0u);
-                mma_tf32(tmem, dah, dbl, idesc, 1u);
-                mma_tf32(tmem, dah, dbh, idesc, 1u);
+                const uint64_t dbh = smem_desc_sw(bh + o, 4096, 512, 1);
+                mma_tf32(tmem, dah, dbh, idesc2, (kt > 0 || j > 0) ? 1u : 0u);   // columns [0, VP): hi x hi, [VP, 2 VP): hi x lo
+                mma_tf32(tmem, dal, dbh, idesc, 1u);                              // columns [0, VP) += lo x hi
             }
             mma_commit(&mbar[s]);
             if (kt == nk - 1) mma_commit(&mbar[2]);
@@ -180,26 +184,27 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_tc_kernel(const float *__re
         const int h = h0 + warp * 32 + lane;
         float *pp = part + (size_t)blockIdx.y * VP * H;
 #pragma unroll
-        for (int c = 0; c < VP / 32; ++c) {
-            uint32_t v[32];
+        for (int c = 0; c < VP / 16; ++c) {
+            uint32_t v[16], w[16];
             if (nk > 0) {
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c * 32, v);
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c * 16, v);
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + VP + c * 16, w);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
+                for (int j = 0; j < 16; ++j) { v[j] = 0u; w[j] = 0u; }
             }
             if (h < H) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c * 32 + j < V) pp[(size_t)(c * 32 + j) * H + h] = __uint_as_float(v[j]);
+                for (int j = 0; j < 16; ++j)
+                    if (c * 16 + j < V) pp[(size_t)(c * 16 + j) * H + h] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(VP) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(2 * VP) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
 {
     constexpr int A_F4 = kBM * kBK / 4;                    // float4 per A tile (one of hi / lo)
     constexpr int B_F4 = VP * kBK / 4;
-    constexpr int TCOLS = VP <= 32 ? 32 : 64;              // TMEM columns are allocated in powers of two (VP = 32, 48, 64)
+    constexpr int TCOLS = VP <= 32 ? 64 : 128;             // 2 VP accumulator columns (below), allocated in powers of two
     extern __shared__ __align__(1024) unsigned char hsm_raw[];
     __shared__ __align__(8) uint64_t mbar[3];              // [0], [1]: stage free again; [2]: accumulator complete
     __shared__ uint32_t tmem_base_s;
@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
     };
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, N >> 3, M >> 4
     constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(VP >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    // the same with N = 2 VP: the lo weight tile follows the hi tile as the next VP class rows, so x_hi x [w_hi | w_lo] is ONE
+    // MMA into 2 VP accumulator columns: two MMAs per K step instead of three, x_hi read from shared memory once, not twice
+    constexpr uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * VP) >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     constexpr int BQ = (B_F4 + kThreads - 1) / kThreads;   // weight float4 per thread and part
     // the weight tile (L2-resident) of a stage is requested one stage ahead: its L2 round trip sat exposed between the
     // transform and the MMAs of every stage in round 1
@@ -229,16 +232,15 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
         //    TMEM accumulators and the epilogue of a block deferred into the next block's second stage: 216 us.
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi), bl = smem_u32(Blo);
+            const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi);
 #pragma unroll
             for (int j = 0; j < kBK / 8; ++j) {            // one MMA covers K = 8 tf32 = 32 bytes inside the 128-byte swizzled rows
                 const uint32_t o = j * 32;
                 // K-major SWIZZLE_128B: SBO = 1024 B between groups of 8 rows; LBO is not used
                 const uint64_t dah = smem_desc_sw(ah + o, 16, 1024, 2), dal = smem_desc_sw(al + o, 16, 1024, 2);
-                const uint64_t dbh = smem_desc_sw(bh + o, 16, 1024, 2), dbl = smem_desc_sw(bl + o, 16, 1024, 2);
-                mma_tf32(tmem, dal, dbh, idesc, (kt > 0 || j > 0) ? 1u : 0u);   // small terms first
-                mma_tf32(tmem, dah, dbl, idesc, 1u);
-                mma_tf32(tmem, dah, dbh, idesc, 1u);
+                const uint64_t dbh = smem_desc_sw(bh + o, 16, 1024, 2);
+                mma_tf32(tmem, dah, dbh, idesc2, (kt > 0 || j > 0) ? 1u : 0u);  // columns [0, VP): hi x hi, [VP, 2 VP): hi x lo
+                mma_tf32(tmem, dal, dbh, idesc, 1u);                             // columns [0, VP) += lo x hi
             }
             mma_commit(&mbar[s]);
             if (kt == nk - 1) mma_commit(&mbar[2]);
@@ -266,11 +268,12 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
     float val[VP];
 #pragma unroll
     for (int h = 0; h < VP / 16; ++h) {
-        uint32_t v[16];
+        uint32_t v[16], w[16];
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + h * 16, v);
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + VP + h * 16, w);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 16; ++j) val[h * 16 + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 16; ++j) val[h * 16 + j] = __uint_as_float(v[j]) + __uint_as_float(w[j]);
     }
 #pragma unroll
     for (int j = 0; j < VP; ++j) val[j] += __ldg(bias + j);
