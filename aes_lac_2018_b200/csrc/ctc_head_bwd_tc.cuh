@@ -4,7 +4,7 @@
 // Both contractions of the backward pass are skinny (V <= 64 on one side) and sit ABOVE the fp32-FMA ridge of a B200
 // (29 FMA per 4 bytes of x), so the round-1 FMA kernels were shared-memory / FMA bound at 17-28 % of the DRAM peak
 // (profiles/r1_head_ncu_final.txt).  Here they run on the 5th-generation tensor cores with the same error-compensated
-// operand split as the forward pass (a = a_hi + a_lo, three MMAs per K-step, fp32 accumulation in TMEM):
+// operand split as the forward pass (a = a_hi + a_lo, three products per K-step -- two MMAs in the weight gradient, where hi x [hi | lo] is one -- fp32 accumulation in TMEM):
 //
 //   head_wgrad_tc_kernel   G^T[h][v] = sum_n (x[n][h] - mu_h) * dl[n][v]        M = 128 features, N = VP classes, K = rows
 //        Both operands lie in HBM with the *non*-contracted index contiguous (x[n][h]: h, dl[n][v]: v), i.e. they are

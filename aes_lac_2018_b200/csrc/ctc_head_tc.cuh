@@ -7,7 +7,7 @@
 // 5th-generation tensor cores have ~30x the throughput needed.  tf32 alone would round the operands to 10 mantissa
 // bits (1e-3 logits; the reference computes in fp32), so each operand is split  a = a_hi + a_lo  (both tf32) and
 //     a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (error ~2^-21 relative per product, fp32 accumulation)
-// -- three MMAs per K-step, still far below the HBM time of the tile.
+// -- three products per K-step (two MMAs: a_hi x [b_hi | b_lo] is one, with N = 2 VP), far below the HBM time of the tile.
 //
 // One CTA = 128 rows of x (UMMA M = 128, cta_group::1), N = VP columns, accumulator = VP TMEM columns.
 // The operands cannot come straight from HBM by TMA: x needs (x - mu) and the hi/lo split first.  So the 256 threads
