@@ -466,6 +466,30 @@ def main():
         except Exception as e:  # noqa: BLE001
             extras["torch_ctc_loss_gpu"] = {"unavailable": repr(e)[:200]}
 
+        # the widening row next to the hot path: the classifier head that produces the activations
+        try:
+            from aes_lac_2018_b200 import SequenceWiseClassifier
+            Th, Bh, Hh = T, 256, 800
+            xh = torch.randn(Th, Bh, Hh, device=dev, requires_grad=True)
+            dlh = torch.randn(Th, Bh, V, device=dev)
+            head = SequenceWiseClassifier(Hh, V).to(dev).train()
+
+            def head_step():
+                xh.grad = None
+                head.forward_time_major(xh).backward(dlh)
+
+            hms = timed_calls(head_step, reps=8, skip=3, do_flush=False)
+            xbytes = Th * Bh * Hh * 4
+            extras["classifier_head"] = {
+                "workload": f"BatchNorm1d({Hh}) + Linear({Hh}, {V}) on T={Th}, B={Bh} rows (x = {xbytes / 1e6:.0f} MB), training forward + backward",
+                "ms_per_step": hms, "x_passes": "2 reads forward, 2 reads + 1 write backward",
+                "hbm_gbs_on_x": 5 * xbytes / (hms * 1e-3) / 1e9,
+                "what": "tcgen05 (3xTF32) forward, weight-gradient and input-gradient kernels of csrc/ctc_head*.cu*; "
+                        "not part of the headline metric"}
+            del xh, dlh, head
+        except Exception as e:  # noqa: BLE001
+            extras["classifier_head"] = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
