@@ -229,7 +229,10 @@ __global__ void __launch_bounds__(kThreads, 2) head_fwd_tc_kernel(const float *_
         //  * row blocks sized for whole waves (109 instead of 128 rows, 5.95 instead of 5.07 waves): 181 us;
         //  * 256-byte L2 fills on the x loads (DRAM locality of the 128-byte row pieces): 175 us;
         //  * persistent CTAs (two per SM) walking the row blocks with the prefetch running across block boundaries, two
-        //    TMEM accumulators and the epilogue of a block deferred into the next block's second stage: 216 us.
+        //    TMEM accumulators and the epilogue of a block deferred into the next block's second stage: 216 us;
+        //  * (against the 168 us of the two-MMA version) the weight tiles by bulk async copies -- cp.async.bulk, the TMA
+        //    engine -- into a ring of four 8 KB slots, requested two stages ahead and awaited by the MMA-issuing thread,
+        //    instead of through registers: 189 us.
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t ah = smem_u32(Ahi), al = smem_u32(Alo), bh = smem_u32(Bhi);
