@@ -40,7 +40,7 @@ for case in range(n_cases):
         eg = float(np.abs(g - og).max())
         same_inf = bool((np.isinf(c) == np.isinf(oc)).all())
         worst["loss"] = max(worst["loss"], el); worst["grad"] = max(worst["grad"], eg)
-        if el > 2e-6 and os.environ.get('FUZZ_VERBOSE'):
+        if (el > 2e-6 or eg > float(os.environ.get('FUZZ_GRAD_NOTE', '1'))) and os.environ.get('FUZZ_VERBOSE'):
             print(f"note case {seed0 + case} mode {mode} bidir {bidir}: V {V} T {T} B {B} lmax {lmax} sigma {sigma} loss err {el:.2e} grad err {eg:.2e} costs {oc[:4].round(3).tolist()} got {c[:4].round(3).tolist()} status {sorted(set(st.tolist()))}", flush=True)
         if el > 1e-4 or eg > 1e-5 or not same_inf or not np.isfinite(g).all():
             bad += 1
