@@ -372,6 +372,7 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
             }
         };
         load_x(0);
+        load_x(1);
         mbar_wait(&mbar[li & 1], (uint32_t)((li >> 1) & 1));       // this block's MMAs are complete: the dl buffer is free
         if (li + 1 < nb) stage_dl(dq);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -379,7 +380,6 @@ head_dgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dl, 
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (tid == 0 && li + 1 < nb) issue_mma(li + 1);    // (runs beside this block's epilogue, into the other accumulator)
-        load_x(1);                                         // in flight while the first half is combined and stored
 #pragma unroll
         for (int c = 0; c < 4; ++c) {                      // 16 rows at a time (32 made ptxas spill under the 128-register cap)
             uint32_t v[16];
