@@ -243,7 +243,8 @@ ctcStatus_t ctc_b200_edit_distance(const int *hyp_tokens_device, long long hyp_s
  * Classifier head that produces the CTC activations: BatchNorm1d(features) followed by Linear(features -> classes,
  * no bias) over the rows = T*B frames of the last recurrent layer.  Replaces `self.fc` of the reference
  * (/root/reference/codes/model.py:177-180, 199-207 and SequenceWiseClassifier, model.py:205-222): 3 + 5 PyTorch
- * kernels over rows x features tensors become two passes over x forward and two backward.  All pointers are DEVICE
+ * kernels over rows x features tensors become two passes over x forward and two backward, the three contractions
+ * on the tensor cores (tcgen05 kind::tf32 with an error-compensated operand split: fp32-level results).  All pointers are DEVICE
  * memory, fp32, dense row-major; calls only enqueue work on `stream`.  classes <= 64, features % 4 == 0.
  *   x              [rows][features]           out / dlogits   [rows][classes]  (rows in T x B order: `out` is the
  *                                                               T x B x V tensor the CTC engine reads)
