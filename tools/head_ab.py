@@ -1,5 +1,4 @@
-"""Per-kernel times of the classifier head at T=750, B=256, H=800, V=29 from torch's profiler (A/B of launch options
-selected by environment variables)."""
+"""Per-kernel times of the classifier head at T=750, B=256, H=800 from torch's profiler.  python tools/head_ab.py [V]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
