@@ -35,3 +35,34 @@ section("ctc_warp_kernel<NS, K, VCH, MAXR, AVS> (fp64 recursion, ratio domain; s
 print("No block barrier (BAR) anywhere: one warp per utterance.  The fp32 kernel has no fp64 on the T-serial chain: its DADD / DMUL / DFMA are the\n"
       "once-per-utterance log Z and the running product of the row sums.  LDGSTS = cp.async staging of the backward operands; (C)REDUX = warp-wide max\n"
       "(row reference of the fp32 kernel, rescale / poison detector of the fp64 kernel); ATOMG = work queue, retired-CTA and workspace-slot counters.")
+
+
+# ---- classifier-head kernels and the packed-fp32 opcodes of the fp32 throughput kernel (from the linked library) ----
+so = os.path.join(ROOT, "aes_lac_2018_b200", "lib", "libctc_b200.so")
+out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+cur, ops = None, collections.defaultdict(collections.Counter)
+for line in out.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        cur = m.group(1)
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+    if m and cur:
+        ops[cur][m.group(1).split(".")[0]] += 1
+
+
+def demangle(f):
+    return subprocess.run(["c++filt", f], capture_output=True, text=True).stdout.strip().split("(")[0].replace("void ", "")
+
+
+print("\nclassifier-head kernels (ctc_head.cu, ctc_head_tc.cuh, ctc_head_bwd_tc.cuh): tensor-core opcodes "
+      "(UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, SYNCS = mbarrier)")
+for f, c in ops.items():
+    if "head_" in f and "tc_kernel" in f and "fold" not in f and "wt_tc" not in f:
+        print(f"  {demangle(f)[:52]:52s} UTCHMMA {c['UTCHMMA']:3d}  UTCBAR {c['UTCBAR']:2d}  LDTM {c['LDTM']:2d}  SYNCS {c['SYNCS']:2d}  "
+              f"LDG {c['LDG']:3d}  STS {c['STS']:3d}  BAR {c['BAR']:2d}  total {sum(c.values())}")
+print("\nfp32 throughput kernel variants: packed single-precision opcodes (FFMA2 / FMUL2 / FADD2, sm_100) against scalar ones")
+for f, c in sorted(ops.items(), key=lambda kv: demangle(kv[0])):
+    if "ctc_warp32_kernel" in f:
+        print(f"  {demangle(f)[:52]:52s} FFMA2 {c['FFMA2']:4d} FMUL2 {c['FMUL2']:4d} FADD2 {c['FADD2']:4d} | FFMA {c['FFMA']:4d} FMUL {c['FMUL']:4d} "
+              f"FADD {c['FADD']:4d} | SHFL {c['SHFL']:4d}  total {sum(c.values())}")
