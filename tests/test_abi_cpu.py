@@ -83,6 +83,26 @@ def test_workspace_size_and_argument_validation(lib):
     assert lib.get_workspace_size(ok.ctypes.data, np.array([4100], np.int32).ctypes.data, 29, 1, _opts(), ctypes.byref(n)) == 0
 
 
+def test_head_workspace_size_and_argument_validation(lib):
+    """ctc_b200_head_workspace_size is pure host arithmetic: sizes for every class padding (32 / 48 / 64), growth with the
+    problem, and the argument checks of the head entry points (no CUDA call is reached)."""
+    n = ctypes.c_size_t(0)
+    sizes = {}
+    for V in (29, 43, 64):
+        assert lib.ctc_b200_head_workspace_size(192000, 800, V, ctypes.byref(n)) == 0
+        sizes[V] = n.value
+        # forward weight tiles (2 * H * VP floats) + input-gradient weight tiles + the row-block partials must fit
+        assert n.value > 4 * 800 * 32 * 2
+    assert sizes[29] < sizes[43] <= sizes[64]
+    assert lib.ctc_b200_head_workspace_size(16, 8, 2, ctypes.byref(n)) == 0 and 0 < n.value < sizes[29]
+    assert lib.ctc_b200_head_workspace_size(100, 802, 29, ctypes.byref(n)) == 2          # features % 4 != 0
+    assert lib.ctc_b200_head_workspace_size(0, 800, 29, ctypes.byref(n)) == 2
+    assert lib.ctc_b200_head_workspace_size(100, 800, 29, None) == 2
+    assert lib.ctc_b200_head_workspace_size(100, 800, 65, ctypes.byref(n)) == 4          # more than 64 classes: not in this build
+    assert b"64" in lib.ctc_b200_last_error()
+    assert lib.ctc_b200_head_forward(None) == 2 and lib.ctc_b200_head_backward(None) == 2
+
+
 def test_compute_rejects_bad_arguments_before_touching_cuda(lib):
     ll = np.array([2], np.int32)
     al = np.array([5], np.int32)
